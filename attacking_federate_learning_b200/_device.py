@@ -1,0 +1,137 @@
+"""Thin torch-side plumbing: device buffers, current stream, and typed calls into the C ABI.
+torch is used for memory and streams only; all arithmetic happens in lib/libafl_b200.so."""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nat
+
+
+def _stream_ptr(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return nat.AFL_F32
+    if t.dtype == torch.bfloat16:
+        return nat.AFL_BF16
+    raise NotImplementedError(f"users_grads dtype {t.dtype}: only float32 and bfloat16 are supported")
+
+
+def check_matrix(G: torch.Tensor):
+    if not (isinstance(G, torch.Tensor) and G.is_cuda):
+        raise TypeError("expected a torch.cuda tensor")
+    if G.dim() != 2 or G.stride(1) != 1:
+        raise ValueError("users_grads must be a 2-D row-major [clients, params] tensor")
+    return G.shape[0], G.shape[1], G.stride(0) if G.shape[0] > 1 else max(G.stride(0), G.shape[1])
+
+
+class Workspace:
+    """Per-device scratch cache (grows on demand, never shrinks)."""
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, device, tag: str, nbytes: int) -> torch.Tensor:
+        key = (str(device), tag)
+        buf = cls._cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            cls._cache[key] = buf
+        return buf
+
+
+def sqdist_partial(G: torch.Tensor, flags: int = 0) -> torch.Tensor:
+    """Partial squared-distance table (float64 [n, n]) of this column shard."""
+    n, d, ld = check_matrix(G)
+    L = nat.lib()
+    with torch.cuda.device(G.device):
+        nbytes = L.afl_sqdist_workspace_bytes(n, d, dtype_code(G), flags)
+        ws = Workspace.get(G.device, "gram", nbytes)
+        d2 = torch.empty((n, n), dtype=torch.float64, device=G.device)
+        nat.check(L.afl_sqdist_partial(G.data_ptr(), n, d, ld, dtype_code(G), d2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       flags, _stream_ptr(G)))
+    return d2
+
+
+def sqdist_to_dist(d2: torch.Tensor) -> torch.Tensor:
+    n = d2.shape[0]
+    dist = torch.empty((n, n), dtype=torch.float32, device=d2.device)
+    with torch.cuda.device(d2.device):
+        nat.check(nat.lib().afl_sqdist_to_dist(d2.data_ptr(), n, dist.data_ptr(), _stream_ptr(d2)))
+    return dist
+
+
+def krum_select(dist: torch.Tensor, users_count: int, corrupted_count: int, want_scores=False):
+    n = dist.shape[0]
+    L = nat.lib()
+    with torch.cuda.device(dist.device):
+        ws = Workspace.get(dist.device, "select", L.afl_select_workspace_bytes(n))
+        idx = torch.empty(1, dtype=torch.int32, device=dist.device)
+        scores = torch.empty(n, dtype=torch.float32, device=dist.device) if want_scores else None
+        nat.check(L.afl_krum_select(dist.data_ptr(), n, users_count, corrupted_count, idx.data_ptr(),
+                                    scores.data_ptr() if want_scores else None, ws.data_ptr(), ws.numel(),
+                                    _stream_ptr(dist)))
+    return (idx, scores) if want_scores else idx
+
+
+def bulyan_select(dist: torch.Tensor, users_count: int, corrupted_count: int) -> torch.Tensor:
+    n = dist.shape[0]
+    L = nat.lib()
+    theta = users_count - 2 * corrupted_count
+    with torch.cuda.device(dist.device):
+        ws = Workspace.get(dist.device, "select", L.afl_select_workspace_bytes(n))
+        sel = torch.empty(max(theta, 1), dtype=torch.int32, device=dist.device)
+        nat.check(L.afl_bulyan_select(dist.data_ptr(), n, users_count, corrupted_count, sel.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _stream_ptr(dist)))
+    return sel[:max(theta, 0)]
+
+
+def trimmed_mean(G: torch.Tensor, corrupted_count: int, row_index: torch.Tensor | None = None) -> torch.Tensor:
+    n, d, ld = check_matrix(G)
+    n_rows = n if row_index is None else int(row_index.numel())
+    out = torch.empty(d, dtype=torch.float32, device=G.device)
+    with torch.cuda.device(G.device):
+        nat.check(nat.lib().afl_trimmed_mean(G.data_ptr(), n, d, ld, dtype_code(G),
+                                             None if row_index is None else row_index.data_ptr(), n_rows,
+                                             corrupted_count, out.data_ptr(), _stream_ptr(G)))
+    return out
+
+
+def mean(G: torch.Tensor) -> torch.Tensor:
+    n, d, ld = check_matrix(G)
+    out = torch.empty(d, dtype=torch.float32, device=G.device)
+    with torch.cuda.device(G.device):
+        nat.check(nat.lib().afl_mean(G.data_ptr(), n, d, ld, dtype_code(G), out.data_ptr(), _stream_ptr(G)))
+    return out
+
+
+def gather_row(G: torch.Tensor, idx_dev: torch.Tensor) -> torch.Tensor:
+    n, d, ld = check_matrix(G)
+    out = torch.empty(d, dtype=torch.float32, device=G.device)
+    with torch.cuda.device(G.device):
+        nat.check(nat.lib().afl_gather_row(G.data_ptr(), n, d, ld, dtype_code(G), idx_dev.data_ptr(), out.data_ptr(),
+                                           _stream_ptr(G)))
+    return out
+
+
+def alie(G_mal: torch.Tensor, z: float, bcast: torch.Tensor | None = None, alias_mean: bool = True):
+    """Returns (crafted, mu, sigma); with alias_mean the returned mu IS crafted (reference aliasing)."""
+    f, d, ld = check_matrix(G_mal)
+    dev = G_mal.device
+    sigma = torch.empty(d, dtype=torch.float32, device=dev)
+    crafted = torch.empty(d, dtype=torch.float32, device=dev)
+    mu = crafted if alias_mean else torch.empty(d, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().afl_alie(G_mal.data_ptr(), f, d, ld, dtype_code(G_mal), float(z), mu.data_ptr(),
+                                     sigma.data_ptr(), crafted.data_ptr(),
+                                     None if bcast is None else bcast.data_ptr(),
+                                     0 if bcast is None else bcast.stride(0), _stream_ptr(G_mal)))
+    return crafted, mu, sigma
+
+
+def momentum_step(weights: torch.Tensor, velocity: torch.Tensor, grads: torch.Tensor, momentum: float, lr: float):
+    d = weights.numel()
+    with torch.cuda.device(weights.device):
+        nat.check(nat.lib().afl_momentum_step(weights.data_ptr(), velocity.data_ptr(), grads.data_ptr(), d,
+                                              float(momentum), float(lr), _stream_ptr(weights)))

@@ -1,0 +1,216 @@
+// HBM-bound column kernels: plain mean (defences.py:13-14), the ALIE mu/sigma/perturb reduction
+// (malicious.py:18-19,35), Krum's row gather, and the server momentum step (server.py:89-90).
+// All of them stream the row-major [n, d] matrix once with 16-byte loads; a thread owns VEC adjacent
+// columns and walks down the rows, so every warp-level load is one contiguous segment of a row.
+#include "afl_common.cuh"
+
+namespace afl {
+namespace colstats {
+
+constexpr int kBlock = 256;
+constexpr int kUnroll = 8;
+
+template <int VEC> struct Pack { float v[VEC]; };
+
+// Load VEC consecutive columns of one row as fp32.  VEC = 4 (fp32, 16 B) or 8 (bf16, 16 B) or 1 (scalar).
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<VEC> load_pack(const T* p);
+template <> __device__ __forceinline__ Pack<4> load_pack<float, 4>(const float* p) {
+  const float4 t = ldg_stream_f4(reinterpret_cast<const float4*>(p));
+  return Pack<4>{{t.x, t.y, t.z, t.w}};
+}
+template <> __device__ __forceinline__ Pack<1> load_pack<float, 1>(const float* p) { return Pack<1>{{__ldg(p)}}; }
+template <> __device__ __forceinline__ Pack<8> load_pack<__nv_bfloat16, 8>(const __nv_bfloat16* p) {
+  const uint4 t = ldg_stream_u4(reinterpret_cast<const uint4*>(p));
+  Pack<8> r;
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = bf16_bits_to_f32(w[i] & 0xFFFFu);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return r;
+}
+template <> __device__ __forceinline__ Pack<1> load_pack<__nv_bfloat16, 1>(const __nv_bfloat16* p) {
+  return Pack<1>{{__bfloat162float(*p)}};
+}
+
+// ---- mean: sequential fp32 row accumulation, then one IEEE division — the order NumPy uses for
+// np.mean(axis=0) on a C-contiguous array, so fp32 results are bit-identical to the reference.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+mean_kernel(const T* __restrict__ G, int n, int64_t d, int64_t ld, float* __restrict__ out) {
+  const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * VEC;
+  if (c0 >= d) return;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  const T* p = G + c0;
+  int r = 0;
+  for (; r + kUnroll <= n; r += kUnroll) {
+    Pack<VEC> t[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) t[u] = load_pack<T, VEC>(p + static_cast<int64_t>(r + u) * ld);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], t[u].v[k]);
+  }
+  for (; r < n; ++r) {
+    Pack<VEC> t = load_pack<T, VEC>(p + static_cast<int64_t>(r) * ld);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], t.v[k]);
+  }
+  const float fn = static_cast<float>(n);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k)
+    if (c0 + k < d) out[c0 + k] = __fdiv_rn(acc[k], fn);
+}
+
+// ---- ALIE: one pass, shifted moments (shift = the first malicious row, so |x - shift| ~ sigma and
+// E[dx^2] - E[dx]^2 does not cancel).  sigma = sqrt(population variance); crafted = mu - z*sigma with
+// the same two roundings as `grads_mean[:] -= num_std * grads_stdev[:]` in fp32.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+alie_kernel(const T* __restrict__ G, int f, int64_t d, int64_t ld, float z, float* __restrict__ mu_out,
+            float* __restrict__ sigma_out, float* __restrict__ crafted_out, float* __restrict__ bcast,
+            int64_t bcast_ld) {
+  const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * VEC;
+  if (c0 >= d) return;
+  const T* p = G + c0;
+  const Pack<VEC> shift = load_pack<T, VEC>(p);
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+  int r = 1;
+  for (; r + kUnroll <= f; r += kUnroll) {
+    Pack<VEC> t[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) t[u] = load_pack<T, VEC>(p + static_cast<int64_t>(r + u) * ld);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float dx = t[u].v[k] - shift.v[k];
+        s1[k] += dx;
+        s2[k] = fmaf(dx, dx, s2[k]);
+      }
+  }
+  for (; r < f; ++r) {
+    Pack<VEC> t = load_pack<T, VEC>(p + static_cast<int64_t>(r) * ld);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float dx = t.v[k] - shift.v[k];
+      s1[k] += dx;
+      s2[k] = fmaf(dx, dx, s2[k]);
+    }
+  }
+  const float inv = 1.0f / static_cast<float>(f);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    if (c0 + k >= d) break;
+    const float m1 = s1[k] * inv;
+    const float mu = shift.v[k] + m1;
+    float var = fmaf(-m1, m1, s2[k] * inv);
+    var = var > 0.f ? var : 0.f;
+    const float sigma = sqrtf(var);
+    const float crafted = __fsub_rn(mu, __fmul_rn(z, sigma));
+    if (sigma_out) sigma_out[c0 + k] = sigma;
+    if (mu_out && mu_out != crafted_out) mu_out[c0 + k] = mu;
+    if (crafted_out) crafted_out[c0 + k] = crafted;
+    if (bcast)
+      for (int rr = 0; rr < f; ++rr) bcast[static_cast<int64_t>(rr) * bcast_ld + c0 + k] = crafted;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+gather_row_kernel(const T* __restrict__ G, int n, int64_t d, int64_t ld, const int* __restrict__ idx_dev,
+                  float* __restrict__ out) {
+  int idx = *idx_dev;
+  if (idx < 0) idx += n;            // the reference's users_grads[-1] when nobody wins
+  if (idx < 0 || idx >= n) return;
+  const T* row = G + static_cast<int64_t>(idx) * ld;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; c < d;
+       c += static_cast<int64_t>(gridDim.x) * kBlock)
+    out[c] = load_pack<T, 1>(row + c).v[0];
+}
+
+__global__ void __launch_bounds__(kBlock)
+momentum_kernel(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, int64_t d, float momentum,
+                float lr) {
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; c < d;
+       c += static_cast<int64_t>(gridDim.x) * kBlock) {
+    // server.py:89  velocity = momentum*velocity - lr*grads  (two products, one subtraction, fp32)
+    const float nv = __fsub_rn(__fmul_rn(momentum, v[c]), __fmul_rn(lr, g[c]));
+    v[c] = nv;
+    w[c] = __fadd_rn(w[c], nv);                      // server.py:90
+  }
+}
+
+static bool vec_ok(const void* G, int64_t ld, int dtype) {
+  const int64_t es = dtype == AFL_F32 ? 4 : 2;
+  return (reinterpret_cast<uintptr_t>(G) % 16 == 0) && ((ld * es) % 16 == 0);
+}
+
+int mean(const void* G, int n, int64_t d, int64_t ld, int dtype, float* out, cudaStream_t stream) {
+  if (!G || !out || n < 1 || d < 1 || ld < d) { set_error("afl_mean: bad argument"); return AFL_ERR_BAD_ARG; }
+  if (dtype != AFL_F32 && dtype != AFL_BF16) { set_error("afl_mean: dtype"); return AFL_ERR_UNSUPPORTED; }
+  const bool v = vec_ok(G, ld, dtype);
+  const int vec = v ? (dtype == AFL_F32 ? 4 : 8) : 1;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(ceil_div64(d, vec), kBlock));
+  if (dtype == AFL_F32) {
+    if (v) mean_kernel<float, 4><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), n, d, ld, out);
+    else mean_kernel<float, 1><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), n, d, ld, out);
+  } else {
+    if (v) mean_kernel<__nv_bfloat16, 8><<<grid, kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), n, d, ld, out);
+    else mean_kernel<__nv_bfloat16, 1><<<grid, kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), n, d, ld, out);
+  }
+  AFL_LAUNCH_CHECK("mean_kernel");
+  return AFL_OK;
+}
+
+int alie(const void* G, int f, int64_t d, int64_t ld, int dtype, double z, float* mu_out, float* sigma_out,
+         float* crafted_out, float* bcast, int64_t bcast_ld, cudaStream_t stream) {
+  if (!G || f < 1 || d < 1 || ld < d || (bcast && bcast_ld < d)) { set_error("afl_alie: bad argument"); return AFL_ERR_BAD_ARG; }
+  if (dtype != AFL_F32 && dtype != AFL_BF16) { set_error("afl_alie: dtype"); return AFL_ERR_UNSUPPORTED; }
+  const bool v = vec_ok(G, ld, dtype);
+  const int vec = v ? (dtype == AFL_F32 ? 4 : 8) : 1;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(ceil_div64(d, vec), kBlock));
+  const float zf = static_cast<float>(z);
+  if (dtype == AFL_F32) {
+    if (v) alie_kernel<float, 4><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
+    else alie_kernel<float, 1><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
+  } else {
+    if (v) alie_kernel<__nv_bfloat16, 8><<<grid, kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
+    else alie_kernel<__nv_bfloat16, 1><<<grid, kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
+  }
+  AFL_LAUNCH_CHECK("alie_kernel");
+  return AFL_OK;
+}
+
+int gather_row(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* idx_dev, float* out,
+               cudaStream_t stream) {
+  if (!G || !idx_dev || !out || n < 1 || d < 1 || ld < d) { set_error("afl_gather_row: bad argument"); return AFL_ERR_BAD_ARG; }
+  int64_t blocks = ceil_div64(d, kBlock);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == AFL_F32)
+    gather_row_kernel<float><<<static_cast<unsigned>(blocks), kBlock, 0, stream>>>(static_cast<const float*>(G), n, d, ld, idx_dev, out);
+  else if (dtype == AFL_BF16)
+    gather_row_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), n, d, ld, idx_dev, out);
+  else { set_error("afl_gather_row: dtype"); return AFL_ERR_UNSUPPORTED; }
+  AFL_LAUNCH_CHECK("gather_row_kernel");
+  return AFL_OK;
+}
+
+int momentum_step(float* w, float* v, const float* g, int64_t d, float momentum, float lr, cudaStream_t stream) {
+  if (!w || !v || !g || d < 1) { set_error("afl_momentum_step: bad argument"); return AFL_ERR_BAD_ARG; }
+  int64_t blocks = ceil_div64(d, kBlock);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  momentum_kernel<<<static_cast<unsigned>(blocks), kBlock, 0, stream>>>(w, v, g, d, momentum, lr);
+  AFL_LAUNCH_CHECK("momentum_kernel");
+  return AFL_OK;
+}
+
+}  // namespace colstats
+}  // namespace afl

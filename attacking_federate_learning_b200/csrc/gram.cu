@@ -1,0 +1,517 @@
+// Pairwise squared distances of the N client rows (reference: defences.py:16-21
+// `_krum_create_distances`, the dominant cost of Krum and Bulyan).
+//
+// tcgen05 path (fp32 input, 16-byte aligned rows):
+//   d2_ij = s_ii + s_jj - 2 s_ij with S = G G^T computed on the 5th-gen tensor cores.
+//   * Operand tiles [128 rows x 32 fp32] are fetched by TMA (SWIZZLE_128B, rows past N zero-filled)
+//     into a multi-stage shared-memory ring.
+//   * fp32 is split as g = hi + lo, hi = the TF32 the tensor core sees (top 10 mantissa bits), lo =
+//     RN_tf32(g - hi).  S ~= hi hi^T + hi lo^T + (hi lo^T)^T: two MMAs per k-step instead of three
+//     (the third product is the transpose of the second and is added in the reduce kernel).  The
+//     dropped lo*lo^T term is <= 2^-20 relative.  The "split" warps compute lo from the TMA tile with
+//     CUDA cores and store it in the same swizzled layout (same byte offsets), so it needs no address
+//     math and feeds tcgen05.mma directly.
+//   * One elected thread issues tcgen05.mma.kind::tf32 (M=128, N=16..128, K=8); accumulators live in
+//     TMEM, double-buffered: every `flush` k-blocks the accumulator is drained by the epilogue warps
+//     (tcgen05.ld) into fp32 registers (round-to-nearest adds) while the MMA continues on the other
+//     buffer.  This bounds the length of the tensor core's internal accumulation chain.
+//   * K (the parameter dimension) is split over CTAs; every CTA writes its partial tile to its own
+//     workspace slot and `reduce` sums the slots in a fixed order in float64 -> bit-reproducible and
+//     identical rows give bit-identical table rows (Krum's [1,0,2,...] tie-break relies on this).
+//
+// SIMT path (any pitch, fp32 or bf16): direct sum of squared fp32 differences, float64 accumulation.
+// Used for misaligned pitches and as an independent check of the tensor path in the tests.
+#include "afl_common.cuh"
+
+namespace afl {
+namespace gram {
+
+constexpr int kBK = 32;                      // fp32 columns per k-block = 128 B = one swizzle row
+constexpr int kTileRows = 128;               // UMMA M, and the largest UMMA N used
+constexpr int kTileBytes = kTileRows * 128;  // 16 KB
+constexpr int kThreads = 512;                // 4 warpgroups
+constexpr int kTmemCols = 512;
+constexpr int kPartElems = 2 * kTileRows * kTileRows;  // per (pair, split): [2][128][128] fp32
+
+struct Params {
+  int n;
+  int tiles;          // T = ceil(n / 128); pairs = T*T
+  int splits;         // K-splits
+  int kblocks;        // ceil(d / 32)
+  int flush;          // k-blocks per TMEM accumulation chain
+  int stages;
+  int stage_bytes;    // 32 KB (T == 1: [A][LO]) or 48 KB ([A][B][LO])
+  int single_pass;
+  int rewrite_hi;
+  float* parts;       // [pairs][splits][2][128][128]
+};
+
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base is only 16 B aligned by
+  // contract, so align by hand (the host adds 1 KB of slack).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], split_bar[8], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
+
+  const int pairs = p.tiles * p.tiles;
+  const int pair = blockIdx.x % pairs;
+  const int split = blockIdx.x / pairs;
+  const int ti = pair / p.tiles, tj = pair % p.tiles;
+  const bool has_b = (ti != tj);
+  const int rows_j = min(kTileRows, p.n - tj * kTileRows);
+  const int nb = (rows_j + 15) & ~15;  // UMMA N
+  const int kb0 = static_cast<int>(static_cast<int64_t>(p.kblocks) * split / p.splits);
+  const int kb1 = static_cast<int>(static_cast<int64_t>(p.kblocks) * (split + 1) / p.splits);
+  const int nkb = kb1 - kb0;
+  const int ngroups = (nkb + p.flush - 1) / p.flush;
+  const uint32_t off_b = kTileBytes;
+  const uint32_t off_lo = (p.stage_bytes == 3 * kTileBytes) ? 2 * kTileBytes : kTileBytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (wg == 0) {
+    setmaxnreg_dec<56>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        const uint64_t pol = (p.tiles == 1) ? policy_evict_first() : policy_evict_normal();
+        for (int it = 0; it < nkb; ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], has_b ? 2 * kTileBytes : kTileBytes);
+          const int col = (kb0 + it) * kBK;
+          tma_load_2d(st, &tmap, &full_bar[s], col, ti * kTileRows, pol);
+          if (has_b) tma_load_2d(st + off_b, &tmap, &full_bar[s], col, tj * kTileRows, pol);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (one thread) =====================
+      const uint32_t idesc = umma_idesc_tf32(kTileRows, nb);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        const int g = it / p.flush;
+        const int in_g = it - g * p.flush;
+        const int b = g & 1;
+        if (in_g == 0) {
+          mbar_wait(&acc_empty[b], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&split_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+          const uint64_t da = umma_desc_sw128(st);
+          const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
+          const uint64_t dl = umma_desc_sw128(st + off_lo);
+          const uint32_t d_hh = tmem_base + static_cast<uint32_t>((b * 2 + 0) * kTileRows);
+          const uint32_t d_x = tmem_base + static_cast<uint32_t>((b * 2 + 1) * kTileRows);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (in_g | ks) != 0;
+            const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 32 bytes (8 tf32) >> 4
+            umma_tf32(d_hh, da + adv, db + adv, idesc, acc);
+            if (!p.single_pass) umma_tf32(d_x, da + adv, dl + adv, idesc, acc);
+          }
+          umma_commit(&empty_bar[s]);
+          if (in_g == p.flush - 1 || it == nkb - 1) umma_commit(&acc_full[b]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wg == 1) {
+    setmaxnreg_dec<56>();
+    // ===================== split warps: lo = RN_tf32(g - hi) =====================
+    const int t = threadIdx.x - 128;
+    const int nchunks_b = nb * 8;           // 16-byte chunks of the B-side tile (rows < nb)
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
+      if (!p.single_pass || p.rewrite_hi) {
+        float4* src = reinterpret_cast<float4*>(st + (has_b ? off_b : 0));
+        float4* dst = reinterpret_cast<float4*>(st + off_lo);
+        for (int c = t; c < nchunks_b; c += 128) {
+          float4 v = src[c];
+          float4 h, l;
+          if (p.rewrite_hi) {
+            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+            src[c] = h;
+          } else {
+            h.x = tf32_trunc(v.x); h.y = tf32_trunc(v.y); h.z = tf32_trunc(v.z); h.w = tf32_trunc(v.w);
+          }
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          dst[c] = l;
+        }
+        if (p.rewrite_hi && has_b) {  // A-side tile is a different row block: round it too
+          float4* a = reinterpret_cast<float4*>(st);
+          for (int c = t; c < kTileRows * 8; c += 128) {
+            float4 v = a[c];
+            v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+            a[c] = v;
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[s]);
+    }
+  } else {
+    setmaxnreg_inc<200>();
+    // ===================== epilogue: drain TMEM chains into fp32 registers =====================
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int a = (warp - 8) >> 2;      // 0: hi*hi^T accumulator, 1: hi*lo^T accumulator
+    float run[kTileRows];
+#pragma unroll
+    for (int i = 0; i < kTileRows; ++i) run[i] = 0.f;
+    const bool active = !(a == 1 && p.single_pass);
+    for (int g = 0; g < ngroups; ++g) {
+      const int b = g & 1;
+      mbar_wait(&acc_full[b], (g >> 1) & 1);
+      tc_fence_after();
+      if (active) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>((b * 2 + a) * kTileRows);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          if (c * 16 < nb) {
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x32b_x16(taddr + c * 16, v0);
+            tmem_ld_32x32b_x16(taddr + c * 16 + 16, v1);   // columns past nb hold stale data; ignored
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              run[c * 16 + i] += __uint_as_float(v0[i]);
+              run[c * 16 + 16 + i] += __uint_as_float(v1[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    float* out = p.parts + (static_cast<size_t>(pair) * p.splits + split) * kPartElems +
+                 static_cast<size_t>(a) * kTileRows * kTileRows + static_cast<size_t>(q * 32 + lane) * kTileRows;
+#pragma unroll
+    for (int c = 0; c < kTileRows; c += 4) {
+      float4 v = make_float4(run[c], run[c + 1], run[c + 2], run[c + 3]);
+      if (c >= nb || !active) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(out + c) = v;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// S_ij = sum over splits (fixed order, float64) of  hh_ij + x_ij + x_ji ;  then d2 = s_ii + s_jj - 2 s_ij.
+__global__ void gram_reduce_kernel(const float* __restrict__ parts, int n, int tiles, int splits,
+                                   double* __restrict__ S) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n) return;
+  const int ti = i >> 7, ii = i & 127, tj = j >> 7, jj = j & 127;
+  const size_t tile = static_cast<size_t>(kTileRows) * kTileRows;
+  const float* pij = parts + static_cast<size_t>(ti * tiles + tj) * splits * kPartElems;
+  const float* pji = parts + static_cast<size_t>(tj * tiles + ti) * splits * kPartElems;
+  double acc = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const float* a = pij + static_cast<size_t>(s) * kPartElems;
+    const float* b = pji + static_cast<size_t>(s) * kPartElems;
+    const double hh = a[ii * kTileRows + jj];
+    const double x1 = a[tile + ii * kTileRows + jj];
+    const double x2 = b[tile + jj * kTileRows + ii];
+    acc += hh + (x1 + x2);   // x1 + x2 is commutative -> S_ij and S_ji get identical bits
+  }
+  S[static_cast<size_t>(i) * n + j] = acc;
+}
+
+__global__ void gram_to_sqdist_kernel(const double* __restrict__ S, int n, double* __restrict__ d2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n) return;
+  double v = 0.0;
+  if (i != j) {
+    const int lo = min(i, j), hi = max(i, j);           // read one triangle so d2 is exactly symmetric
+    v = (S[static_cast<size_t>(lo) * n + lo] + S[static_cast<size_t>(hi) * n + hi]) -
+        2.0 * S[static_cast<size_t>(lo) * n + hi];
+  }
+  d2[static_cast<size_t>(i) * n + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT difference kernel: block = 16x16 threads, tile = 32 x 32 client pairs, k-chunks of 32.
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float load_elem(const T* p);
+template <> __device__ __forceinline__ float load_elem<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_elem<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sqdist_simt_kernel(const T* __restrict__ G, int n, int64_t d, int64_t ld, int splits, double* __restrict__ part) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int tiles = (n + 31) / 32;
+  const int ti = blockIdx.x / tiles, tj = blockIdx.x % tiles;
+  if (tj > ti) return;                                  // lower triangle (incl. diagonal tiles)
+  const int split = blockIdx.y;
+  const int64_t chunks = (d + 31) / 32;
+  const int64_t c0 = chunks * split / splits, c1 = chunks * (split + 1) / splits;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int64_t c = c0; c < c1; ++c) {
+    const int64_t col0 = c * 32;
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int r = e >> 5, k = e & 31;
+      const int64_t col = col0 + k;
+      const int ra = ti * 32 + r, rb = tj * 32 + r;
+      As[r][k] = (ra < n && col < d) ? load_elem<T>(G + static_cast<int64_t>(ra) * ld + col) : 0.f;
+      Bs[r][k] = (rb < n && col < d) ? load_elem<T>(G + static_cast<int64_t>(rb) * ld + col) : 0.f;
+    }
+    __syncthreads();
+    float part32[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const float df = As[ty * 2 + u][k] - Bs[tx * 2 + v][k];   // fl32(g_i - g_j), as the reference
+          part32[u][v] = fmaf(df, df, part32[u][v]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) acc[u][v] += static_cast<double>(part32[u][v]);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int i = ti * 32 + ty * 2 + u, j = tj * 32 + tx * 2 + v;
+      if (i < n && j < n && j < i) part[(static_cast<size_t>(split) * n + i) * n + j] = acc[u][v];
+    }
+}
+
+__global__ void sqdist_simt_reduce_kernel(const double* __restrict__ part, int n, int splits,
+                                          double* __restrict__ d2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n) return;
+  double v = 0.0;
+  if (i != j) {
+    const int hi = max(i, j), lo = min(i, j);
+    for (int s = 0; s < splits; ++s) v += part[(static_cast<size_t>(s) * n + hi) * n + lo];
+  }
+  d2[static_cast<size_t>(i) * n + j] = v;
+}
+
+__global__ void sqdist_to_dist_kernel(const double* __restrict__ d2, int n, float* __restrict__ dist) {
+  const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= static_cast<size_t>(n) * n) return;
+  const int i = static_cast<int>(e / n), j = static_cast<int>(e % n);
+  const double v = d2[e];
+  dist[e] = (i == j) ? 0.f : static_cast<float>(sqrt(v > 0.0 ? v : 0.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct Plan {
+  bool tensor;
+  int tiles, splits, stages, stage_bytes, flush;
+  int simt_splits;
+  size_t parts_bytes, s_bytes, total;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+static bool tensor_eligible(const void* G, int n, int64_t d, int64_t ld, int dtype) {
+  return dtype == AFL_F32 && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(G) % 16 == 0) && n >= 1 && d >= 1 &&
+         n <= 4096 && d < (int64_t(1) << 31) - 64;
+}
+
+static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, int flags) {
+  Plan pl{};
+  pl.tensor = !(flags & AFL_GRAM_FORCE_SIMT) && tensor_eligible(G, n, d, ld, dtype);
+  const int sms = sm_count();
+  if (pl.tensor) {
+    pl.tiles = (n + kTileRows - 1) / kTileRows;
+    const int pairs = pl.tiles * pl.tiles;
+    const int kblocks = static_cast<int>((d + kBK - 1) / kBK);
+    // choose K-splits so that pairs*splits fills an integer number of waves as well as possible
+    int best = 1; double best_eff = -1.0;
+    for (int w = 1; w <= 4; ++w) {
+      int s = (sms * w) / pairs; if (s < 1) s = 1;
+      if (s > kblocks) s = kblocks;
+      const int ctas = pairs * s;
+      const double eff = static_cast<double>(ctas) / (static_cast<double>((ctas + sms - 1) / sms) * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+      if (s == kblocks) break;
+    }
+    pl.splits = env_int("AFL_GRAM_SPLITS", best);
+    if (pl.splits > kblocks) pl.splits = kblocks;
+    if (pl.splits < 1) pl.splits = 1;
+    pl.stage_bytes = (pl.tiles == 1) ? 2 * kTileBytes : 3 * kTileBytes;
+    pl.stages = (pl.tiles == 1) ? 6 : 4;
+    pl.flush = env_int("AFL_GRAM_FLUSH", 8);
+    if (pl.flush < 1) pl.flush = 1;
+    pl.parts_bytes = static_cast<size_t>(pairs) * pl.splits * kPartElems * sizeof(float);
+    pl.s_bytes = align_up(static_cast<size_t>(n) * n * sizeof(double), 256);
+    pl.total = pl.parts_bytes + pl.s_bytes;
+  } else {
+    const int t32 = (n + 31) / 32;
+    int64_t chunks = (d + 31) / 32;
+    int s = (sms * 8) / (t32 * (t32 + 1) / 2); if (s < 1) s = 1;
+    if (s > chunks) s = static_cast<int>(chunks);
+    if (s > 1024) s = 1024;
+    pl.simt_splits = s;
+    pl.total = static_cast<size_t>(s) * n * n * sizeof(double);
+  }
+  pl.total = align_up(pl.total, 256);
+  return pl;
+}
+
+size_t workspace_bytes(int n, int64_t d, int dtype, int flags) {
+  // Upper bound that holds for either path (the pointer alignment is unknown here).
+  Plan a = make_plan(reinterpret_cast<const void*>(16), n, d, 4, dtype, flags & ~AFL_GRAM_FORCE_SIMT);
+  Plan b = make_plan(reinterpret_cast<const void*>(16), n, d, 4, dtype, flags | AFL_GRAM_FORCE_SIMT);
+  return (a.total > b.total ? a.total : b.total) + 256;
+}
+
+int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out, void* ws, size_t ws_bytes,
+                   int flags, cudaStream_t stream) {
+  if (!G || !d2_out || n < 1 || d < 1 || ld < d) { set_error("afl_sqdist_partial: bad argument"); return AFL_ERR_BAD_ARG; }
+  if (dtype != AFL_F32 && dtype != AFL_BF16) { set_error("afl_sqdist_partial: dtype"); return AFL_ERR_UNSUPPORTED; }
+  Plan pl = make_plan(G, n, d, ld, dtype, flags);
+  if ((flags & AFL_GRAM_FORCE_TCGEN05) && !pl.tensor) {
+    set_error("afl_sqdist_partial: tcgen05 path needs fp32, 16-byte aligned base and pitch %% 4 == 0, n <= 4096");
+    return AFL_ERR_UNSUPPORTED;
+  }
+  if (!ws || ws_bytes < pl.total || (reinterpret_cast<uintptr_t>(ws) % 256) != 0) {
+    set_error("afl_sqdist_partial: workspace too small or misaligned (%zu < %zu)", ws_bytes, pl.total);
+    return AFL_ERR_WORKSPACE;
+  }
+  const dim3 rblock(128), rgrid((n + 127) / 128, n);
+  if (pl.tensor) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return AFL_ERR_CUDA; }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+    const cuuint32_t box[2] = {kBK, kTileRows};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(G), gdim, gstride, box, estride,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", static_cast<int>(r)); return AFL_ERR_CUDA; }
+    Params p{};
+    p.n = n; p.tiles = pl.tiles; p.splits = pl.splits; p.kblocks = static_cast<int>((d + kBK - 1) / kBK);
+    p.flush = pl.flush; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
+    p.single_pass = (flags & AFL_GRAM_SINGLE_PASS) ? 1 : 0;
+    p.rewrite_hi = (flags & AFL_GRAM_REWRITE_HI) ? 1 : 0;
+    p.parts = static_cast<float*>(ws);
+    double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
+    const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      AFL_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    gram_tcgen05_kernel<<<pl.tiles * pl.tiles * pl.splits, kThreads, smem, stream>>>(tmap, p);
+    AFL_LAUNCH_CHECK("gram_tcgen05_kernel");
+    gram_reduce_kernel<<<rgrid, rblock, 0, stream>>>(p.parts, n, pl.tiles, pl.splits, S);
+    AFL_LAUNCH_CHECK("gram_reduce_kernel");
+    gram_to_sqdist_kernel<<<rgrid, rblock, 0, stream>>>(S, n, d2_out);
+    AFL_LAUNCH_CHECK("gram_to_sqdist_kernel");
+  } else {
+    const int t32 = (n + 31) / 32;
+    double* part = static_cast<double*>(ws);
+    const dim3 grid(t32 * t32, pl.simt_splits);
+    if (dtype == AFL_F32)
+      sqdist_simt_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(G), n, d, ld, pl.simt_splits, part);
+    else
+      sqdist_simt_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), n, d, ld,
+                                                                   pl.simt_splits, part);
+    AFL_LAUNCH_CHECK("sqdist_simt_kernel");
+    sqdist_simt_reduce_kernel<<<rgrid, rblock, 0, stream>>>(part, n, pl.simt_splits, d2_out);
+    AFL_LAUNCH_CHECK("sqdist_simt_reduce_kernel");
+  }
+  return AFL_OK;
+}
+
+int sqdist_to_dist(const double* d2, int n, float* dist, cudaStream_t stream) {
+  if (!d2 || !dist || n < 1) { set_error("afl_sqdist_to_dist: bad argument"); return AFL_ERR_BAD_ARG; }
+  const size_t total = static_cast<size_t>(n) * n;
+  sqdist_to_dist_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(d2, n, dist);
+  AFL_LAUNCH_CHECK("sqdist_to_dist_kernel");
+  return AFL_OK;
+}
+
+}  // namespace gram
+}  // namespace afl

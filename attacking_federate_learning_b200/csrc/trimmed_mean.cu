@@ -1,0 +1,410 @@
+// Coordinate-wise trimmed mean around the median (reference: defences.py:44-52) — also Bulyan's
+// second stage (defences.py:70) through `row_index`.
+//
+// Per column:  med = median of the N values (even N: fl32 mean of the two middle ones);
+//              dev = fl32(x - med); keep the k devs of smallest |dev|, ties in client (row) order;
+//              out = fl32(fl32(sum(kept)/k) + med).
+//
+// Layout / mapping
+//   * A CTA owns a tile of 64 bytes per row (16 fp32 or 32 bf16 columns) x all rows.  Rows are read
+//     with coalesced 16-byte loads (4 lanes per row segment) and scattered into shared memory in a
+//     [word-column][slot-group][lane] order with an XOR on the slot-in-group index, so that both the
+//     staging stores (STS.32) and the per-column reads (LDS.128) are bank-conflict free.
+//   * One warp then owns one word-column: lane l holds rows l, l+32, l+64, ... in registers
+//     (S = ceil(N/32) "slots"), so every pass over the column is pure register arithmetic plus one
+//     warp reduction.  Rows past N are staged as +inf and never counted.
+//   * Selection is an interpolation search on counts: a pass counts #{x < p} (and, for the |dev|
+//     threshold, the sum of the devs below p); the first pivot comes from the column's mean / sigma,
+//     later ones from the measured counts.  As soon as the bracket [lo, hi) holds <= 32 elements they
+//     are compacted (ballot) to one per lane and bitonic-sorted with the row index as secondary key,
+//     which makes the reference's stable tie rule exact.  A min/max bisection fallback guarantees
+//     termination for any data (heavy ties, non-Gaussian columns); a tie group larger than a warp
+//     (ALIE's f identical rows) is resolved in row order with ballots.
+#include "afl_common.cuh"
+
+namespace afl {
+namespace tmean {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kWordCols = 16;             // 32-bit words per staged row (64 bytes)
+constexpr float kInf = __builtin_huge_valf();
+
+struct Params {
+  const void* G;
+  const int* row_index;   // may be null
+  float* out;
+  int64_t d, ld;
+  int n_rows;             // participating rows
+  int n_total;            // rows of G (bounds for row_index)
+  int keep;               // effective number of kept devs (python slice semantics applied), >= 0
+  float med_density;      // 0.39894228 * n      (ranks per unit value at the centre of a unit Gaussian)
+  float key_q;            // Gaussian guess of the |dev| threshold in sigmas
+  float key_density;      // 2 * phi(key_q) * n  (ranks per unit |dev| at that threshold, unit sigma)
+  int vec_ok;
+};
+
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Ascending bitonic sort of one (key, id, payload) triple per lane; (key, id) pairs must be distinct.
+__device__ __forceinline__ void warp_sort32(float& key, int& id, float& payload, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, key, j);
+      const int oi = __shfl_xor_sync(0xffffffffu, id, j);
+      const float op = __shfl_xor_sync(0xffffffffu, payload, j);
+      const bool up = (lane & k) == 0;
+      const bool lower = (lane & j) == 0;
+      const bool other_less = (ok < key) || (ok == key && oi < id);
+      const bool take = (lower == up) ? other_less : !other_less;
+      if (take) { key = ok; id = oi; payload = op; }
+    }
+  }
+}
+
+// true row of register index ri (registers hold each 4-slot group permuted by jx, see staging)
+__device__ __forceinline__ int row_of(int ri, int jx, int lane) { return (((ri & ~3) | ((ri & 3) ^ jx)) << 5) + lane; }
+
+template <bool KEYS> __device__ __forceinline__ float keyof(float v) { return KEYS ? fabsf(v) : v; }
+
+// One counting pass: c = #{key(v) < p}; for KEYS also s = sum of v over those elements.
+template <int S, bool KEYS>
+__device__ __forceinline__ void count_pass(const float (&v)[S], float p, int& c, float& s) {
+  int cc = 0;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    const bool b = keyof<KEYS>(v[i]) < p;
+    cc += b ? 1 : 0;
+    if (KEYS) ss += b ? v[i] : 0.f;
+  }
+  c = warp_sum_i(cc);
+  if (KEYS) s = warp_sum(ss);
+}
+
+// Selection over a register-resident column.
+//   KEYS = false : returns the order statistics of ranks r1 <= r2 (r2 <= r1 + 1) in a, b.
+//   KEYS = true  : v holds devs, key = |dev|; r1 == r2 == keep-1; returns in `a` the sum of the `keep`
+//                  devs of smallest key with ties resolved in row order.
+template <int S, bool KEYS>
+__device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, int r2, float p0, float density,
+                                            int lane, int jx, float& a, float& b) {
+  float lo = -kInf, hi = kInf;
+  int c_lo = 0, c_hi = n;
+  float sum_lo = 0.f;
+  bool model = (density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf);
+  float p = p0;
+  a = b = __int_as_float(0x7fc00000);
+  for (int iter = 0; iter < 96; ++iter) {
+    const int inb = c_hi - c_lo;
+    if (inb <= 32) {
+      // ---- compact the bracket to one element per lane, sort by (key, row), read off the answer
+      float ck = kInf, cp = 0.f;
+      int cid = 0x7fffff00 + lane;
+      int base = 0;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const float k = keyof<KEYS>(v[i]);
+        const bool in = (k >= lo) && (k < hi);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (m) {
+          const int pos = base + __popc(m & ((1u << lane) - 1u));
+          // hand element to lane `pos`: every lane checks whether some source lane targets it
+          const int row = row_of(i, jx, lane);
+#pragma unroll 1
+          for (unsigned mm = m; mm; mm &= mm - 1) {
+            const int src = __ffs(mm) - 1;
+            const int dst = __shfl_sync(0xffffffffu, pos, src);
+            const float kv = __shfl_sync(0xffffffffu, k, src);
+            const float pv = __shfl_sync(0xffffffffu, v[i], src);
+            const int rv = __shfl_sync(0xffffffffu, row, src);
+            if (lane == dst) { ck = kv; cp = pv; cid = rv; }
+          }
+          base += __popc(m);
+        }
+      }
+      warp_sort32(ck, cid, cp, lane);
+      if (!KEYS) {
+        a = __shfl_sync(0xffffffffu, ck, r1 - c_lo);
+        b = __shfl_sync(0xffffffffu, ck, r2 - c_lo);
+      } else {
+        const int take = r1 + 1 - c_lo;             // kept candidates = first `take` in (key,row) order
+        float part = (lane < take) ? cp : 0.f;
+        a = sum_lo + warp_sum(part);
+      }
+      return;
+    }
+    if (iter >= 4 || !model) {
+      // ---- fallback: bisect between the actual extremes of the bracket (guaranteed progress)
+      float vmin = kInf, vmax = -kInf;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const float k = keyof<KEYS>(v[i]);
+        const bool in = (k >= lo) && (k < hi);
+        vmin = in ? fminf(vmin, k) : vmin;
+        vmax = in ? fmaxf(vmax, k) : vmax;
+      }
+      vmin = warp_min_f(vmin);
+      vmax = warp_max_f(vmax);
+      if (!(vmin < vmax)) {
+        // every element of the bracket has the same key (a tie group wider than a warp)
+        if (!KEYS) { a = b = vmin; return; }
+        int need = r1 + 1 - c_lo;                    // how many of the tied elements are kept
+        float part = 0.f;
+        int before = 0;
+#pragma unroll
+        for (int g = 0; g < S; g += 4) {
+          unsigned bm[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bm[q] = __ballot_sync(0xffffffffu, fabsf(v[g + q]) == vmin);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {           // true slot order inside the group
+            const int q = kk ^ jx;
+            const unsigned m = q == 0 ? bm[0] : q == 1 ? bm[1] : q == 2 ? bm[2] : bm[3];
+            const float val = q == 0 ? v[g] : q == 1 ? v[g + 1] : q == 2 ? v[g + 2] : v[g + 3];
+            if ((m >> lane) & 1u) {
+              const int rank = before + __popc(m & ((1u << lane) - 1u));
+              if (rank < need) part += val;
+            }
+            before += __popc(m);
+          }
+        }
+        a = sum_lo + warp_sum(part);
+        return;
+      }
+      p = 0.5f * vmin + 0.5f * vmax;
+      if (!(p > vmin)) p = vmax;
+      model = false;
+    }
+    int c;
+    float s = 0.f;
+    count_pass<S, KEYS>(v, p, c, s);
+    if (c <= r1) { lo = p; c_lo = c; sum_lo = s; }
+    else if (c > r2) { hi = p; c_hi = c; }
+    else {
+      // p separates the two middle order statistics (even N median only)
+      float below = -kInf, above = kInf;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        below = (v[i] < p) ? fmaxf(below, v[i]) : below;
+        above = (v[i] >= p) ? fminf(above, v[i]) : above;
+      }
+      a = warp_max_f(below);
+      b = warp_min_f(above);
+      return;
+    }
+    if (model) {
+      // aim just past the target on the far side so that the next pass closes the bracket
+      float step;
+      if (c <= r1) { const float gap = static_cast<float>(r2 + 1 - c); step = (gap + 3.f + 0.25f * gap) / density; }
+      else { const float gap = static_cast<float>(c - r1); step = -(gap + 3.f + 0.25f * gap) / density; }
+      float np = p + step;
+      if (!(np > lo && np < hi)) {
+        if (lo > -kInf && hi < kInf) np = 0.5f * lo + 0.5f * hi;
+        if (!(np > lo && np < hi)) model = false;
+      }
+      p = np;
+    }
+  }
+}
+
+template <int S, bool BF16>
+__global__ void __launch_bounds__(kThreads)
+trimmed_mean_kernel(const Params P) {
+  extern __shared__ __align__(16) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots]
+  constexpr int kGroups = S / 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int es = BF16 ? 2 : 4;
+  const int cols_per_tile = BF16 ? 32 : 16;
+  const int64_t col0 = static_cast<int64_t>(blockIdx.x) * cols_per_tile;
+  const uint32_t sentinel = BF16 ? 0x7F807F80u : 0x7F800000u;
+  const uint8_t* base = static_cast<const uint8_t*>(P.G);
+
+  // ---------------- staging: coalesced 16-byte row-segment loads -> swizzled smem ----------------
+  constexpr int kIters = (32 * S * 4) / kThreads;      // S/2
+  constexpr int kBatch = kIters < 4 ? kIters : 4;
+#pragma unroll 1
+  for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+    uint4 val[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int idx = (it0 + u) * kThreads + tid;
+      const int r = idx >> 2, j = idx & 3;
+      uint4 t = make_uint4(sentinel, sentinel, sentinel, sentinel);
+      if (r < P.n_rows) {
+        int gr = P.row_index ? P.row_index[r] : r;
+        gr = gr < 0 ? gr + P.n_total : gr;
+        const int64_t c = col0 + static_cast<int64_t>(j) * (16 / es);
+        const uint8_t* src = base + (static_cast<int64_t>(gr) * P.ld + c) * es;
+        if (P.vec_ok && c + (16 / es) <= P.d) {
+          t = ldg_stream_u4(reinterpret_cast<const uint4*>(src));
+        } else {
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+          if (BF16) {
+            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (c + e < P.d) w[e >> 1] |= static_cast<uint32_t>(s16[e]) << ((e & 1) * 16);
+          } else {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c + e < P.d) w[e] = s32[e];
+          }
+          t = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      val[u] = t;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int idx = (it0 + u) * kThreads + tid;
+      const int r = idx >> 2, j = idx & 3;
+      const int slot = r >> 5, l = r & 31, m = slot >> 2, k = slot & 3;
+      const uint32_t w[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int cw = 4 * j + t;
+        tile[((cw * kGroups + m) * 32 + l) * 4 + (k ^ j)] = w[t];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- per-column work: one warp per word-column ----------------
+  const int n = P.n_rows;
+  const float fn = static_cast<float>(n);
+#pragma unroll 1
+  for (int cw = warp; cw < kWordCols; cw += kWarps) {
+    const int jx = (cw >> 2) & 3;
+    uint32_t wv[S];
+    const uint4* t4 = reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane;
+#pragma unroll
+    for (int m = 0; m < kGroups; ++m) {
+      const uint4 t = t4[m * 32];
+      wv[4 * m] = t.x; wv[4 * m + 1] = t.y; wv[4 * m + 2] = t.z; wv[4 * m + 3] = t.w;
+    }
+#pragma unroll 1
+    for (int half = 0; half < (BF16 ? 2 : 1); ++half) {
+      const int64_t col = col0 + (BF16 ? 2 * cw + half : cw);
+      if (col >= P.d) break;                         // warp-uniform
+      float x[S];
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+        x[i] = BF16 ? __uint_as_float(half ? (wv[i] & 0xFFFF0000u) : (wv[i] << 16)) : __uint_as_float(wv[i]);
+
+      // mean / sigma of the column (pivot model only; never enters the result)
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const bool ok = x[i] < kInf;
+        s1 += ok ? x[i] : 0.f;
+        s2 += ok ? x[i] * x[i] : 0.f;
+      }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      const float mean = s1 / fn;
+      const float var = fmaxf(s2 / fn - mean * mean, 0.f);
+      const float sd = sqrtf(var);
+
+      // median (np.median: even N -> mean of the two middle order statistics, fp32)
+      float a, b;
+      warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, a, b);
+      const float med = ((n & 1) != 0) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
+
+      float res;
+      if (P.keep <= 0) {
+        res = __int_as_float(0x7fc00000);           // np.mean([]) is nan
+      } else {
+#pragma unroll
+        for (int i = 0; i < S; ++i) x[i] = __fsub_rn(x[i], med);      // devs; padded rows stay +inf
+        float total, unused;
+        warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, total, unused);
+        res = __fadd_rn(__fdiv_rn(total, static_cast<float>(P.keep)), med);
+      }
+      if (lane == 0) P.out[col] = res;
+    }
+  }
+}
+
+static double norm_ppf(double pr) {   // Acklam's rational approximation, |error| < 1.2e-9
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                             1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                             6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                             -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double dd[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                              3.754408661907416e+00};
+  if (pr <= 0.0) return -8.0;
+  if (pr >= 1.0) return 8.0;
+  if (pr < 0.02425) {
+    const double q = sqrt(-2.0 * log(pr));
+    return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+           ((((dd[0] * q + dd[1]) * q + dd[2]) * q + dd[3]) * q + 1.0);
+  }
+  if (pr > 1.0 - 0.02425) {
+    const double q = sqrt(-2.0 * log(1.0 - pr));
+    return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+           ((((dd[0] * q + dd[1]) * q + dd[2]) * q + dd[3]) * q + 1.0);
+  }
+  const double q = pr - 0.5, r = q * q;
+  return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+         (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
+}
+
+template <int S>
+static int launch(const Params& P, int dtype, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(S) * 2048;
+  const int cols = dtype == AFL_BF16 ? 32 : 16;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(P.d, cols));
+  if (dtype == AFL_BF16) {
+    AFL_CUDA(cudaFuncSetAttribute(trimmed_mean_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    trimmed_mean_kernel<S, true><<<grid, kThreads, smem, stream>>>(P);
+  } else {
+    AFL_CUDA(cudaFuncSetAttribute(trimmed_mean_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    trimmed_mean_kernel<S, false><<<grid, kThreads, smem, stream>>>(P);
+  }
+  AFL_LAUNCH_CHECK("trimmed_mean_kernel");
+  return AFL_OK;
+}
+
+int trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* row_index, int n_rows,
+                 int corrupted_count, float* out, cudaStream_t stream) {
+  if (!G || !out || n < 1 || d < 1 || ld < d || n_rows < 1) { set_error("afl_trimmed_mean: bad argument"); return AFL_ERR_BAD_ARG; }
+  if (dtype != AFL_F32 && dtype != AFL_BF16) { set_error("afl_trimmed_mean: dtype"); return AFL_ERR_UNSUPPORTED; }
+  if (n_rows > 1024) {
+    set_error("afl_trimmed_mean: at most 1024 participating rows are supported by the register-resident kernel (got %d)", n_rows);
+    return AFL_ERR_UNSUPPORTED;
+  }
+  // number_to_consider = rows - f - 1, then Python slice semantics for sorted(...)[:k]   (defences.py:45,50)
+  const int k = n_rows - corrupted_count - 1;
+  const int keep = k >= 0 ? (k < n_rows ? k : n_rows) : (n_rows + k > 0 ? n_rows + k : 0);
+  Params P{};
+  P.G = G; P.row_index = row_index; P.out = out; P.d = d; P.ld = ld; P.n_rows = n_rows; P.n_total = n; P.keep = keep;
+  P.med_density = 0.3989422804f * static_cast<float>(n_rows);
+  const double frac = keep > 0 ? (static_cast<double>(keep) - 0.5) / n_rows : 0.5;
+  const double q = norm_ppf(0.5 * (1.0 + (frac < 0.999999 ? frac : 0.999999)));
+  P.key_q = static_cast<float>(q);
+  P.key_density = static_cast<float>(2.0 * 0.3989422804014327 * exp(-0.5 * q * q) * n_rows);
+  const int64_t es = dtype == AFL_F32 ? 4 : 2;
+  P.vec_ok = (reinterpret_cast<uintptr_t>(G) % 16 == 0) && ((ld * es) % 16 == 0);
+  if (n_rows <= 128) return launch<4>(P, dtype, stream);
+  if (n_rows <= 256) return launch<8>(P, dtype, stream);
+  if (n_rows <= 512) return launch<16>(P, dtype, stream);
+  return launch<32>(P, dtype, stream);
+}
+
+}  // namespace tmean
+}  // namespace afl

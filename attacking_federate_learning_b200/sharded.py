@@ -1,0 +1,82 @@
+"""D-sharded multi-GPU aggregation: one process per GPU (torch.distributed), GPU r holds the column
+block G[:, r*D/P:(r+1)*D/P].  Coordinate-wise rules (trimmed mean, mean, ALIE, Bulyan stage 2) need
+no communication.  Krum / Bulyan need exactly one sum-all-reduce of the N x N float64 table of partial
+squared distances (squared sums add across shards; the square root is taken after the reduce), after
+which selection runs replicated and deterministically on every rank.
+
+The per-shard arithmetic is delegated to a `kernels` object; the default binds the CUDA library.
+(Tests inject a NumPy stand-in to exercise the sharding / collective logic on CPU with gloo.)
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(dim: int, world: int, rank: int, align: int = 32):
+    """Contiguous column block of `rank`, boundaries aligned to `align` columns (tile width)."""
+    blocks = (dim + align - 1) // align
+    b0 = blocks * rank // world
+    b1 = blocks * (rank + 1) // world
+    return min(b0 * align, dim), min(b1 * align, dim)
+
+
+class NativeKernels:
+    def __getattr__(self, name):
+        from . import _device as dev
+        return getattr(dev, name)
+
+
+class ShardedAggregator:
+    def __init__(self, group=None, kernels=None):
+        self.group = group
+        self.k = kernels if kernels is not None else NativeKernels()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    # -- the single exchange step of the path
+    def _allreduce_table(self, d2):
+        if self.world > 1:
+            dist.all_reduce(d2, op=dist.ReduceOp.SUM, group=self.group)
+        return d2
+
+    def distances(self, G_shard):
+        return self.k.sqdist_to_dist(self._allreduce_table(self.k.sqdist_partial(G_shard)))
+
+    def krum(self, G_shard, users_count, corrupted_count, return_index=False):
+        if not return_index:
+            assert users_count >= 2 * corrupted_count + 1, ('users_count>=2*corrupted_count + 3', users_count, corrupted_count)
+        idx = int(self.k.krum_select(self.distances(G_shard), users_count, corrupted_count).reshape(-1)[0].item())
+        return idx if return_index else G_shard[idx]
+
+    def bulyan(self, G_shard, users_count, corrupted_count, return_selection=False):
+        assert users_count >= 4 * corrupted_count + 3
+        sel = self.k.bulyan_select(self.distances(G_shard), users_count, corrupted_count)
+        out = self.k.trimmed_mean(G_shard, 2 * corrupted_count, row_index=sel)
+        return (out, sel) if return_selection else out
+
+    def trimmed_mean(self, G_shard, users_count, corrupted_count):
+        return self.k.trimmed_mean(G_shard, corrupted_count)
+
+    def no_defense(self, G_shard, users_count=None, corrupted_count=None):
+        return self.k.mean(G_shard)
+
+    def alie(self, G_shard, corrupted_count, num_std):
+        crafted, _, _ = self.k.alie(G_shard[:corrupted_count], num_std, G_shard if G_shard.dtype == torch.float32 else None)
+        return crafted
+
+    def defend(self, name, G_shard, users_count, corrupted_count):
+        return {"Krum": self.krum, "TrimmedMean": self.trimmed_mean, "NoDefense": self.no_defense,
+                "Bulyan": self.bulyan}[name](G_shard, users_count, corrupted_count)
+
+    def gather_output(self, out_shard, dim):
+        """Optional: replicate the full [D] result on every rank (all_gather of the slices)."""
+        if self.world == 1:
+            return out_shard
+        sizes = [shard_bounds(dim, self.world, r)[1] - shard_bounds(dim, self.world, r)[0] for r in range(self.world)]
+        width = max(sizes)                                   # all_gather needs equal-sized pieces
+        mine = torch.zeros(width, dtype=out_shard.dtype, device=out_shard.device)
+        mine[:out_shard.numel()] = out_shard
+        parts = [torch.empty(width, dtype=out_shard.dtype, device=out_shard.device) for _ in sizes]
+        dist.all_gather(parts, mine, group=self.group)
+        return torch.cat([p[:s] for p, s in zip(parts, sizes)])
