@@ -107,7 +107,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if (++spins > (1u << 22)) {
       printf("afl: mbarrier timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, (void*)bar, parity);
       __trap();

@@ -1,0 +1,260 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(lib/libafl_b200.so); the checker is oracle/ref_numpy.py and the golden vectors minted from the
+unmodified reference (tests/golden/golden_v1.npz).
+
+Tolerances (from BASELINE.json north_star): selected client indices bit-exact; aggregated gradients
+within 1e-5 relative fp32.  "Relative" for a vector whose entries pass through zero is measured
+(i) norm-wise: ||out-ref||_2 <= 1e-5 ||ref||_2 and (ii) element-wise with rtol=1e-5 plus an absolute
+floor of 1e-6 x the column scale, which is the size of the reference's own fp32 rounding noise.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+from oracle import ref_numpy as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(got, ref, scale):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-6 * scale)
+    assert np.linalg.norm(got - ref) <= RTOL * max(np.linalg.norm(ref), 1e-30) + 1e-7 * scale * np.sqrt(ref.size)
+
+
+def hetero(rng, n, d):
+    return (0.1 * rng.standard_normal(d) + np.exp(0.25 * rng.standard_normal((n, 1))) * rng.standard_normal((n, d))).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from attacking_federate_learning_b200 import defences, malicious, _device, _native
+    _native.lib()
+    return defences, malicious, _device, _native
+
+
+# ------------------------------------------------------------------ golden vectors from the reference
+@pytest.mark.parametrize("name", golden_names("krum_idx"))
+def test_golden_krum(api, golden, name):
+    D, _, dev, nat = api
+    G = golden[f"{name}/G"]; f = int(golden[f"{name}/f"]); n = len(G)
+    want = int(golden[f"{name}/krum_idx"])
+    Gd = torch.from_numpy(G).cuda()
+    assert D.krum(Gd, n, f, return_index=True) == want                       # device path (SIMT: odd pitch)
+    if G.shape[1] % 4 == 0:
+        dist = dev.sqdist_to_dist(dev.sqdist_partial(Gd, nat.GRAM_FORCE_TCGEN05))
+        assert int(dev.krum_select(dist, n, f).item()) == want                # tensor-core path
+    if n >= 2 * f + 1:
+        row = D.krum(G, n, f)                                                 # host-buffer C entry point
+        assert np.shares_memory(row, G) and np.array_equal(row, G[want])
+
+
+@pytest.mark.parametrize("name", golden_names("dist"))
+def test_golden_distances(api, golden, name):
+    D, _, dev, nat = api
+    G = golden[f"{name}/G"]
+    table = D._krum_create_distances(torch.from_numpy(G).cuda())
+    assert table.keys() == list(golden[f"{name}/order"])
+    np.testing.assert_allclose(table.dense.cpu().numpy(), golden[f"{name}/dist"], rtol=2e-6, atol=1e-7)
+    # the mapping protocol of the reference's dict-of-dicts
+    if len(G) >= 2:
+        assert list(table[1].keys()) == [v for v in range(len(G)) if v != 1]
+
+
+@pytest.mark.parametrize("name", golden_names("tm"))
+def test_golden_trimmed_mean(api, golden, name):
+    D, *_ = api
+    G = golden[f"{name}/G"]; f = int(golden[f"{name}/f"]); n = len(G)
+    want = golden[f"{name}/tm"]
+    scale = float(np.abs(G).mean()) + 1e-30
+    close(D.trimmed_mean(torch.from_numpy(G).cuda(), n, f).cpu().numpy(), want, scale)
+    close(D.trimmed_mean(G, n, f), want, scale)                               # host path
+
+
+@pytest.mark.parametrize("name", golden_names("bulyan"))
+def test_golden_bulyan(api, golden, name):
+    D, *_ = api
+    G = golden[f"{name}/G"]; f = int(golden[f"{name}/f"]); n = len(G)
+    out, sel = D.bulyan(torch.from_numpy(G).cuda(), n, f, return_selection=True)
+    assert sel.cpu().tolist() == list(golden[f"{name}/bulyan_sel"])
+    scale = float(np.abs(G).mean())
+    close(out.cpu().numpy(), golden[f"{name}/bulyan"], scale)
+    close(D.bulyan(G, n, f), golden[f"{name}/bulyan"], scale)
+
+
+@pytest.mark.parametrize("name", golden_names("mean"))
+def test_golden_mean_bit_exact(api, golden, name):
+    D, *_ = api
+    G = golden[f"{name}/G"]
+    assert np.array_equal(D.no_defense(torch.from_numpy(G).cuda(), len(G), 0).cpu().numpy(), golden[f"{name}/mean"])
+    assert np.array_equal(D.no_defense(G, len(G), 0), golden[f"{name}/mean"])
+
+
+@pytest.mark.parametrize("nm", ["a", "b", "c", "d"])
+def test_golden_alie(api, golden, nm):
+    _, M, *_ = api
+    rows = golden[f"alie_{nm}/rows"]; z = float(golden[f"alie_{nm}/z"])
+
+    class U:
+        def __init__(self, g): self.grads = g; self.original_params = None; self.learning_rate = None
+    for to_dev in (False, True):
+        users = [U(torch.from_numpy(r.copy()).cuda() if to_dev else r.copy()) for r in rows]
+        att = M.DriftAttack(z); att.attack(users)
+        mean = att.grads_mean.cpu().numpy() if to_dev else att.grads_mean
+        sd = att.grads_stdev.cpu().numpy() if to_dev else att.grads_stdev
+        np.testing.assert_allclose(sd, golden[f"alie_{nm}/stdev"], rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(mean, golden[f"alie_{nm}/mean"], rtol=RTOL, atol=1e-6)
+        g0 = users[0].grads.cpu().numpy() if to_dev else users[0].grads
+        np.testing.assert_allclose(g0, golden[f"alie_{nm}/grads0"], rtol=RTOL, atol=1e-6)
+        if z != 0:
+            assert all(u.grads is users[0].grads for u in users) and users[0].grads is att.grads_mean
+
+
+# ------------------------------------------------------------------ seeded random inputs vs the oracle
+@pytest.mark.parametrize("n,d,f,seed", [(10, 79510, 2, 0), (100, 40000, 24, 1), (37, 12345, 8, 2), (130, 8192, 30, 3),
+                                        (300, 4096, 70, 4)])
+def test_krum_matches_oracle(api, n, d, f, seed):
+    D, _, dev, nat = api
+    rng = np.random.default_rng(seed)
+    G = hetero(rng, n, d)
+    Gd = torch.from_numpy(G).cuda()
+    table64 = orc.pairwise_distances_f64(G)
+    want, margin = orc.krum_select(table64, orc.visit_order(n), n, f, dtype=np.float64, with_margin=True)
+    assert margin > 1e-5, "test input has a near-tie; pick another seed"
+    assert D.krum(Gd, n, f, return_index=True) == want
+    row = D.krum(Gd, n, f)
+    assert row.data_ptr() == Gd[want].data_ptr()                              # a view, like the reference
+    # the tensor-core table agrees with the float64 arbiter far inside the oracle's own fp32 noise
+    Gp = torch.zeros((n, (d + 3) // 4 * 4), device="cuda")[:, :d]; Gp.copy_(Gd)
+    d2 = dev.sqdist_partial(Gp, nat.GRAM_FORCE_TCGEN05).cpu().numpy()
+    off = ~np.eye(n, dtype=bool)
+    rel = np.abs(d2 - table64 ** 2)[off] / (table64 ** 2)[off]
+    assert rel.max() < 2e-6, rel.max()
+    d2s = dev.sqdist_partial(Gd, nat.GRAM_FORCE_SIMT).cpu().numpy()
+    assert (np.abs(d2s - table64 ** 2)[off] / (table64 ** 2)[off]).max() < 1e-6
+
+
+def test_identical_rows_tie_goes_to_user_1(api):
+    """ALIE makes rows 0..f-1 the same array; exact ties resolve in the reference's dict order."""
+    D, M, dev, nat = api
+    rng = np.random.default_rng(5)
+    n, d, f = 40, 8192, 9
+    G = 5.0 * hetero(rng, n, d); G[:f] = 0.002 * G[f]
+    Gd = torch.from_numpy(G).cuda()
+    for flags in (nat.GRAM_FORCE_TCGEN05, nat.GRAM_FORCE_SIMT):
+        d2 = dev.sqdist_partial(Gd, flags)
+        assert float(d2[:f, :f].abs().max()) == 0.0
+        dist = dev.sqdist_to_dist(d2)
+        assert all(torch.equal(dist[0, f:], dist[i, f:]) for i in range(1, f))
+        assert int(dev.krum_select(dist, n, f).item()) == 1
+    assert orc.krum(G, n, f, return_index=True) == 1
+
+
+@pytest.mark.parametrize("n,f,seed", [(31, 7, 0), (100, 24, 1), (203, 50, 2), (500, 100, 3)])
+def test_bulyan_selection_matches_oracle(api, n, f, seed):
+    D, _, dev, _ = api
+    rng = np.random.default_rng(100 + seed)
+    d = 256
+    G = hetero(rng, n, d)
+    if seed % 2:
+        G[:f] = orc.alie_attack([G[i].copy() for i in range(f)], 1.0)[0]      # identical malicious rows
+    table = orc.pairwise_distances_f32(G)
+    want, margins = orc.bulyan_select(table.astype(np.float64), n, f, dtype=np.float64, with_margins=True)
+    sel = dev.bulyan_select(torch.from_numpy(table).cuda(), n, f).cpu().tolist()
+    assert sel == want, (min(margins),)
+    if min(m for m in margins if m > 0) > 1e-5:
+        assert sel == orc.bulyan_select(table, n, f)                          # and the fp32 reference arithmetic
+
+
+@pytest.mark.parametrize("n,d,f,bf16,seed", [(10, 5000, 2, False, 0), (100, 3000, 24, False, 1), (101, 3000, 24, False, 2),
+                                             (300, 2048, 100, False, 3), (1000, 1024, 240, False, 4),
+                                             (1000, 1024, 240, True, 5), (64, 4096, 15, True, 6), (999, 515, 0, False, 7)])
+def test_trimmed_mean_matches_oracle(api, n, d, f, bf16, seed):
+    D, *_ = api
+    rng = np.random.default_rng(200 + seed)
+    G = hetero(rng, n, d)
+    Gd = torch.from_numpy(G).cuda()
+    if bf16:
+        Gd = Gd.bfloat16(); G = Gd.float().cpu().numpy()                     # the oracle sees the upcast bf16 values
+    got = D.trimmed_mean(Gd, n, f).cpu().numpy()
+    close(got, orc.trimmed_mean(G, n, f), float(np.abs(G).mean()))
+
+
+def test_trimmed_mean_under_alie_ties(api):
+    D, *_ = api
+    rng = np.random.default_rng(77)
+    n, d, f = 1000, 768, 240
+    G = hetero(rng, n, d)
+    G[:f] = orc.alie_attack([G[i].copy() for i in range(f)], 1.5)[0]          # 240 identical values per column
+    got = D.trimmed_mean(torch.from_numpy(G).cuda(), n, f).cpu().numpy()
+    close(got, orc.trimmed_mean(G, n, f), float(np.abs(G).mean()))
+
+
+def test_full_bulyan_and_alie_pipeline(api):
+    D, M, *_ = api
+    rng = np.random.default_rng(31)
+    n, d, f = 103, 6000, 25
+    G = hetero(rng, n, d)
+    Gd = torch.from_numpy(G).cuda()
+    att = M.DriftAttack(1.5)
+    crafted = att.attack_rows(Gd, f)
+    ref_crafted, _, ref_sd = orc.alie_attack([G[i].copy() for i in range(f)], 1.5)
+    np.testing.assert_allclose(crafted.cpu().numpy(), ref_crafted, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(att.grads_stdev.cpu().numpy(), ref_sd, rtol=RTOL)
+    assert torch.equal(Gd[0], Gd[f - 1]) and torch.equal(Gd[0], crafted)
+    G = Gd.cpu().numpy()
+    out, sel = D.bulyan(Gd, n, f, return_selection=True)
+    table64 = orc.pairwise_distances_f64(G)
+    assert sel.cpu().tolist() == orc.bulyan_select(table64, n, f, dtype=np.float64)
+    close(out.cpu().numpy(), orc.trimmed_mean(G[sel.cpu().numpy()], len(sel), 2 * f), float(np.abs(G).mean()))
+
+
+def test_server_defend_step(api):
+    from attacking_federate_learning_b200.server import AggregationServer
+    rng = np.random.default_rng(8)
+    n, d = 10, 79510
+    srv = AggregationServer(n, d, mal_prop=0.24, learning_rate=0.1, momentum=0.9)
+    G = hetero(rng, n, d)
+
+    class U:
+        def __init__(self, g): self.grads = g
+    srv.collect_gradients([U(g) for g in G])
+    w0 = srv.current_weights.cpu().numpy().copy(); v0 = srv.velocity.cpu().numpy().copy()
+    g = srv.defend('Krum')
+    idx = orc.krum(G, n, int(n * 0.24), return_index=True)
+    assert np.array_equal(g.cpu().numpy(), G[idx])
+    w1, v1 = orc.momentum_step(w0, v0, G[idx], np.float32(0.9), np.float32(0.1))
+    np.testing.assert_allclose(srv.velocity.cpu().numpy(), v1, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(srv.current_weights.cpu().numpy(), w1, rtol=1e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_properties_at_scale(api):
+    D, _, dev, nat = api
+    n, d, f = 100, 2_000_000, 24
+    g = torch.Generator(device="cuda").manual_seed(5)
+    G = torch.randn(n, d, generator=g, device="cuda") * torch.exp(0.25 * torch.randn(n, 1, generator=g, device="cuda"))
+    idx = D.krum(G, n, f, return_index=True)
+    perm = torch.randperm(n, generator=g, device="cuda")
+    idx_p = D.krum(G[perm].contiguous(), n, f, return_index=True)
+    assert int(perm[idx_p]) == idx                                            # permutation equivariance
+    d2 = dev.sqdist_partial(G)
+    halves = dev.sqdist_partial(G[:, :d // 2]) + dev.sqdist_partial(G[:, d // 2:])
+    assert float(((d2 - halves).abs() / d2.clamp_min(1)).max()) < 1e-6        # shard partials add up
+    assert torch.equal(d2, d2.T) and float(torch.diagonal(d2).abs().max()) == 0.0
+    ex = torch.cdist(G[:8, :200000].double(), G[:8, :200000].double()) ** 2
+    got = dev.sqdist_partial(G[:8, :200000].contiguous())
+    assert float(((got - ex).abs() / ex.clamp_min(1)).max()) < 2e-6
+    # trimmed mean: constant columns, shift equivariance, bounded by the column range
+    n2, d2c = 1000, 200_000
+    X = torch.randn(n2, d2c, generator=g, device="cuda")
+    tm = D.trimmed_mean(X, n2, 240)
+    assert bool(((tm >= X.min(0).values) & (tm <= X.max(0).values)).all())
+    C = torch.full((n2, 4096), 3.25, device="cuda")
+    assert torch.equal(D.trimmed_mean(C, n2, 240), torch.full((4096,), 3.25, device="cuda"))
+    assert float((D.trimmed_mean(X + 2.0, n2, 240) - (tm + 2.0)).abs().max()) < 1e-5
