@@ -22,6 +22,8 @@ SIGNATURES = {
     "afl_last_error": (C.c_char_p, []),
     "afl_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "afl_launch_count": (C.c_uint64, []),
+    "afl_profile_enable": (_i, [_i]),
+    "afl_profile_read": (_i, [C.c_char_p, C.POINTER(_d), C.POINTER(_i)]),
     "afl_mean": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp]),
     "afl_sqdist_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "afl_sqdist_partial": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _sz, _i, _vp]),
@@ -78,3 +80,14 @@ def check(rc: int):
 
 def launch_count() -> int:
     return int(lib().afl_launch_count())
+
+
+def profile_enable(on: bool):
+    check(lib().afl_profile_enable(1 if on else 0))
+
+
+def profile_read(kernel: str):
+    """(total_ms, launches) of the recorded launches of `kernel`; clears them."""
+    ms, cnt = _d(0.0), _i(0)
+    check(lib().afl_profile_read(kernel.encode(), C.byref(ms), C.byref(cnt)))
+    return ms.value, cnt.value

@@ -34,6 +34,13 @@ void count_launch(int n = 1);
 
 int sm_count();
 
+// Optional CUDA-event bracket around a kernel launch (active only after afl_profile_enable(1)).
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+  const char* name_; cudaStream_t stream_; void* rec_;
+};
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

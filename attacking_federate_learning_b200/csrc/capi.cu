@@ -4,6 +4,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "afl_common.cuh"
 
@@ -23,6 +25,46 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return AFL_ERR_CUDA;
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+// ---- event-based kernel timing -----------------------------------------------------------------
+struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof_recs;
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : name_(name), stream_(stream), rec_(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec* r = new ProfRec{name, nullptr, nullptr};
+  if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) { delete r; return; }
+  cudaEventRecord(r->e0, stream);
+  rec_ = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec_) return;
+  ProfRec* r = static_cast<ProfRec*>(rec_);
+  cudaEventRecord(r->e1, stream_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof_recs.push_back(r);
+}
+static int profile_read(const char* kernel, double* total_ms, int* launches) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  double tot = 0.0; int cnt = 0;
+  std::vector<ProfRec*> keep;
+  for (ProfRec* r : g_prof_recs) {
+    if (r->name != kernel) { keep.push_back(r); continue; }
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r->e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r->e0, r->e1);
+    cudaEventDestroy(r->e0); cudaEventDestroy(r->e1);
+    delete r;
+    if (e != cudaSuccess) return cuda_fail(e, "afl_profile_read", __FILE__, __LINE__);
+    tot += ms; ++cnt;
+  }
+  g_prof_recs.swap(keep);
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = cnt;
+  return AFL_OK;
+}
 
 int sm_count() {
   static int cached = 0;
@@ -221,6 +263,12 @@ int afl_device_info(int* sms, int* cc_major, int* cc_minor, size_t* free_bytes, 
   if (free_bytes) *free_bytes = f;
   if (total_bytes) *total_bytes = t;
   return AFL_OK;
+}
+
+int afl_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); return AFL_OK; }
+int afl_profile_read(const char* kernel, double* total_ms, int* launches) {
+  if (!kernel) { set_error("afl_profile_read: kernel is NULL"); return AFL_ERR_BAD_ARG; }
+  return profile_read(kernel, total_ms, launches);
 }
 
 int afl_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, float* out, void* stream) {

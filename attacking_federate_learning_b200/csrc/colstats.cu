@@ -159,6 +159,7 @@ int mean(const void* G, int n, int64_t d, int64_t ld, int dtype, float* out, cud
   const bool v = vec_ok(G, ld, dtype);
   const int vec = v ? (dtype == AFL_F32 ? 4 : 8) : 1;
   const unsigned grid = static_cast<unsigned>(ceil_div64(ceil_div64(d, vec), kBlock));
+  ProfScope ps("mean", stream);
   if (dtype == AFL_F32) {
     if (v) mean_kernel<float, 4><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), n, d, ld, out);
     else mean_kernel<float, 1><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), n, d, ld, out);
@@ -178,6 +179,7 @@ int alie(const void* G, int f, int64_t d, int64_t ld, int dtype, double z, float
   const int vec = v ? (dtype == AFL_F32 ? 4 : 8) : 1;
   const unsigned grid = static_cast<unsigned>(ceil_div64(ceil_div64(d, vec), kBlock));
   const float zf = static_cast<float>(z);
+  ProfScope ps("alie", stream);
   if (dtype == AFL_F32) {
     if (v) alie_kernel<float, 4><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
     else alie_kernel<float, 1><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);

@@ -483,7 +483,10 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
       AFL_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    gram_tcgen05_kernel<<<pl.tiles * pl.tiles * pl.splits, kThreads, smem, stream>>>(tmap, p);
+    {
+      ProfScope ps("gram_tcgen05", stream);
+      gram_tcgen05_kernel<<<pl.tiles * pl.tiles * pl.splits, kThreads, smem, stream>>>(tmap, p);
+    }
     AFL_LAUNCH_CHECK("gram_tcgen05_kernel");
     gram_reduce_kernel<<<rgrid, rblock, 0, stream>>>(p.parts, n, pl.tiles, pl.splits, S);
     AFL_LAUNCH_CHECK("gram_reduce_kernel");
@@ -493,11 +496,14 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     const int t32 = (n + 31) / 32;
     double* part = static_cast<double*>(ws);
     const dim3 grid(t32 * t32, pl.simt_splits);
-    if (dtype == AFL_F32)
-      sqdist_simt_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(G), n, d, ld, pl.simt_splits, part);
-    else
-      sqdist_simt_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), n, d, ld,
-                                                                   pl.simt_splits, part);
+    {
+      ProfScope ps("sqdist_simt", stream);
+      if (dtype == AFL_F32)
+        sqdist_simt_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(G), n, d, ld, pl.simt_splits, part);
+      else
+        sqdist_simt_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), n, d, ld,
+                                                                     pl.simt_splits, part);
+    }
     AFL_LAUNCH_CHECK("sqdist_simt_kernel");
     sqdist_simt_reduce_kernel<<<rgrid, rblock, 0, stream>>>(part, n, pl.simt_splits, d2_out);
     AFL_LAUNCH_CHECK("sqdist_simt_reduce_kernel");

@@ -245,6 +245,7 @@ static int run_sort(const float* dist, int n, int take, void* ws, size_t ws_byte
   }
   SortWs w = carve(ws, n);
   int P = 1; while (P < n) P <<= 1;
+  ProfScope ps("row_sort", stream);
   row_sort_kernel<<<n, 256, static_cast<size_t>(P) * sizeof(unsigned long long), stream>>>(dist, n, take, w);
   AFL_LAUNCH_CHECK("row_sort_kernel");
   *out = w;
@@ -278,6 +279,7 @@ int bulyan_select(const float* dist, int n, int users_count, int f, int* sel_out
   SortWs w;
   int rc = run_sort(dist, n, python_slice_take(users_count - f, n - 1), ws, ws_bytes, stream, &w);
   if (rc) return rc;
+  ProfScope ps("bulyan_rounds", stream);
   bulyan_rounds_kernel<<<1, 1024, 0, stream>>>(dist, n, f, theta, w, sel_out);
   AFL_LAUNCH_CHECK("bulyan_rounds_kernel");
   return AFL_OK;

@@ -369,6 +369,7 @@ static int launch(const Params& P, int dtype, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(S) * 2048;
   const int cols = dtype == AFL_BF16 ? 32 : 16;
   const unsigned grid = static_cast<unsigned>(ceil_div64(P.d, cols));
+  ProfScope ps("trimmed_mean", stream);
   if (dtype == AFL_BF16) {
     AFL_CUDA(cudaFuncSetAttribute(trimmed_mean_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     trimmed_mean_kernel<S, true><<<grid, kThreads, smem, stream>>>(P);

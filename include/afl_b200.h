@@ -65,6 +65,14 @@ int afl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_by
 /* Number of kernel launches this library has issued since load (all threads). */
 uint64_t afl_launch_count(void);
 
+/* ---- in-library kernel timing (measurement aid for bench.py) -----------------------------------
+ * While enabled, the dominant kernel of every entry point is bracketed by CUDA events on the stream it
+ * is launched on.  afl_profile_read(name, ...) waits for the recorded events of kernel `name`
+ * ("gram_tcgen05", "sqdist_simt", "trimmed_mean", "alie", "mean", "row_sort", "bulyan_rounds"),
+ * returns their summed duration and launch count, and forgets them. */
+int afl_profile_enable(int on);
+int afl_profile_read(const char* kernel, double* total_ms, int* launches);
+
 /* ---- plain mean:  defences.py:13-14  no_defense -> np.mean(users_grads, axis=0) --------------- */
 int afl_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, float* out, void* stream);
 
