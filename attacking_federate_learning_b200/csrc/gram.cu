@@ -31,6 +31,7 @@ constexpr int kTileRows = 128;               // UMMA M, and the largest UMMA N u
 constexpr int kTileBytes = kTileRows * 128;  // 16 KB
 constexpr int kThreads = 512;                // 4 warpgroups
 constexpr int kTmemCols = 512;
+constexpr int kChunk = 4;                    // k-blocks per contiguous K chunk (4 x 128 B = 512 B per row)
 constexpr int kPartElems = 2 * kTileRows * kTileRows;  // per (pair, split): [2][128][128] fp32
 
 struct Params {
@@ -47,10 +48,9 @@ struct Params {
 };
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// round-to-nearest (ties away) to TF32 precision = cvt.rna.tf32.f32, done on the integer pipe
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -74,9 +74,15 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   const bool has_b = (ti != tj);
   const int rows_j = min(kTileRows, p.n - tj * kTileRows);
   const int nb = (rows_j + 15) & ~15;  // UMMA N
-  const int kb0 = static_cast<int>(static_cast<int64_t>(p.kblocks) * split / p.splits);
-  const int kb1 = static_cast<int>(static_cast<int64_t>(p.kblocks) * (split + 1) / p.splits);
-  const int nkb = kb1 - kb0;
+  // K assignment: k-blocks are grouped in chunks of kChunk (512 contiguous bytes per row); split s owns
+  // chunks s, s+splits, s+2*splits, ...  At any moment the CTAs of one tile pair therefore read a
+  // contiguous band of every row (DRAM pages are consumed whole) instead of 128-byte pieces that are
+  // megabytes apart.
+  const int nchunks_total = (p.kblocks + kChunk - 1) / kChunk;
+  const int my_chunks = split < nchunks_total ? (nchunks_total - split + p.splits - 1) / p.splits : 0;
+  int nkb = my_chunks * kChunk;
+  if (my_chunks > 0 && split + (my_chunks - 1) * p.splits == nchunks_total - 1)
+    nkb -= nchunks_total * kChunk - p.kblocks;          // the globally last chunk may be short
   const int ngroups = (nkb + p.flush - 1) / p.flush;
   const uint32_t off_b = kTileBytes;
   const uint32_t off_lo = (p.stage_bytes == 3 * kTileBytes) ? 2 * kTileBytes : kTileBytes;
@@ -115,7 +121,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], has_b ? 2 * kTileBytes : kTileBytes);
-          const int col = (kb0 + it) * kBK;
+          const int col = ((split + (it / kChunk) * p.splits) * kChunk + (it % kChunk)) * kBK;
           tma_load_2d(st, &tmap, &full_bar[s], col, ti * kTileRows, pol);
           if (has_b) tma_load_2d(st + off_b, &tmap, &full_bar[s], col, tj * kTileRows, pol);
         }
@@ -169,17 +175,24 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       if (!p.single_pass || p.rewrite_hi) {
         float4* src = reinterpret_cast<float4*>(st + (has_b ? off_b : 0));
         float4* dst = reinterpret_cast<float4*>(st + off_lo);
-        for (int c = t; c < nchunks_b; c += 128) {
-          float4 v = src[c];
-          float4 h, l;
-          if (p.rewrite_hi) {
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            src[c] = h;
-          } else {
-            h.x = tf32_trunc(v.x); h.y = tf32_trunc(v.y); h.z = tf32_trunc(v.z); h.w = tf32_trunc(v.w);
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)                       // all loads first: 8 LDS.128 in flight per thread
+          if (t + u * 128 < nchunks_b) v[u] = src[t + u * 128];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (t + u * 128 < nchunks_b) {
+            float4 h, l;
+            if (p.rewrite_hi) {
+              h.x = tf32_rna(v[u].x); h.y = tf32_rna(v[u].y); h.z = tf32_rna(v[u].z); h.w = tf32_rna(v[u].w);
+              src[t + u * 128] = h;
+            } else {
+              h.x = tf32_trunc(v[u].x); h.y = tf32_trunc(v[u].y); h.z = tf32_trunc(v[u].z); h.w = tf32_trunc(v[u].w);
+            }
+            l.x = tf32_rna(v[u].x - h.x); l.y = tf32_rna(v[u].y - h.y);
+            l.z = tf32_rna(v[u].z - h.z); l.w = tf32_rna(v[u].w - h.w);
+            dst[t + u * 128] = l;
           }
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          dst[c] = l;
         }
         if (p.rewrite_hi && has_b) {  // A-side tile is a different row block: round it too
           float4* a = reinterpret_cast<float4*>(st);
@@ -403,7 +416,7 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
   if (pl.tensor) {
     pl.tiles = (n + kTileRows - 1) / kTileRows;
     const int pairs = pl.tiles * pl.tiles;
-    const int kblocks = static_cast<int>((d + kBK - 1) / kBK);
+    const int kblocks = (static_cast<int>((d + kBK - 1) / kBK) + kChunk - 1) / kChunk;   // in chunks
     // choose K-splits so that pairs*splits fills an integer number of waves as well as possible
     int best = 1; double best_eff = -1.0;
     for (int w = 1; w <= 4; ++w) {
@@ -419,7 +432,7 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     if (pl.splits < 1) pl.splits = 1;
     pl.stage_bytes = (pl.tiles == 1) ? 2 * kTileBytes : 3 * kTileBytes;
     pl.stages = (pl.tiles == 1) ? 6 : 4;
-    pl.flush = env_int("AFL_GRAM_FLUSH", 8);
+    pl.flush = env_int("AFL_GRAM_FLUSH", 4);
     if (pl.flush < 1) pl.flush = 1;
     pl.parts_bytes = static_cast<size_t>(pairs) * pl.splits * kPartElems * sizeof(float);
     pl.s_bytes = align_up(static_cast<size_t>(n) * n * sizeof(double), 256);

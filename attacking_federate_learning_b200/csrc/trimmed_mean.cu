@@ -56,22 +56,10 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
-// Ascending bitonic sort of one (key, id, payload) triple per lane; (key, id) pairs must be distinct.
-__device__ __forceinline__ void warp_sort32(float& key, int& id, float& payload, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const float ok = __shfl_xor_sync(0xffffffffu, key, j);
-      const int oi = __shfl_xor_sync(0xffffffffu, id, j);
-      const float op = __shfl_xor_sync(0xffffffffu, payload, j);
-      const bool up = (lane & k) == 0;
-      const bool lower = (lane & j) == 0;
-      const bool other_less = (ok < key) || (ok == key && oi < id);
-      const bool take = (lower == up) ? other_less : !other_less;
-      if (take) { key = ok; id = oi; payload = op; }
-    }
-  }
+// Monotone map float -> uint32 (total order incl. negatives; NaN sorts last for positive payloads).
+__device__ __forceinline__ uint32_t ord_bits(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
 // true row of register index ri (registers hold each 4-slot group permuted by jx, see staging)
@@ -79,7 +67,7 @@ __device__ __forceinline__ int row_of(int ri, int jx, int lane) { return (((ri &
 
 template <bool KEYS> __device__ __forceinline__ float keyof(float v) { return KEYS ? fabsf(v) : v; }
 
-// One counting pass: c = #{key(v) < p}; for KEYS also s = sum of v over those elements.
+// One counting pass: c = #{key(v) < p} (warp total); for KEYS also s = this LANE's sum of v over those elements.
 template <int S, bool KEYS>
 __device__ __forceinline__ void count_pass(const float (&v)[S], float p, int& c, float& s) {
   int cc = 0;
@@ -91,7 +79,7 @@ __device__ __forceinline__ void count_pass(const float (&v)[S], float p, int& c,
     if (KEYS) ss += b ? v[i] : 0.f;
   }
   c = warp_sum_i(cc);
-  if (KEYS) s = warp_sum(ss);
+  if (KEYS) s = ss;                 // lane-local partial; reduced once at the very end
 }
 
 // Selection over a register-resident column.
@@ -100,7 +88,7 @@ __device__ __forceinline__ void count_pass(const float (&v)[S], float p, int& c,
 //                  devs of smallest key with ties resolved in row order.
 template <int S, bool KEYS>
 __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, int r2, float p0, float density,
-                                            int lane, int jx, float& a, float& b) {
+                                            int lane, int jx, uint32_t* scratch, float& a, float& b) {
   float lo = -kInf, hi = kInf;
   int c_lo = 0, c_hi = n;
   float sum_lo = 0.f;
@@ -110,9 +98,13 @@ __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, 
   for (int iter = 0; iter < 96; ++iter) {
     const int inb = c_hi - c_lo;
     if (inb <= 32) {
-      // ---- compact the bracket to one element per lane, sort by (key, row), read off the answer
-      float ck = kInf, cp = 0.f;
-      int cid = 0x7fffff00 + lane;
+      // ---- compact the bracket into this warp's smem scratch (ballot prefix), then rank every
+      // candidate by counting (key, row) pairs below it: independent broadcast loads, no shuffles.
+      unsigned long long* sk = reinterpret_cast<unsigned long long*>(scratch);      // [32] (ord(key) << 32) | row
+      float* sp = reinterpret_cast<float*>(scratch + 64);                            // [32] payload
+      sk[lane] = ~0ull;
+      sp[lane] = 0.f;
+      __syncwarp();
       int base = 0;
 #pragma unroll
       for (int i = 0; i < S; ++i) {
@@ -120,29 +112,29 @@ __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, 
         const bool in = (k >= lo) && (k < hi);
         const unsigned m = __ballot_sync(0xffffffffu, in);
         if (m) {
-          const int pos = base + __popc(m & ((1u << lane) - 1u));
-          // hand element to lane `pos`: every lane checks whether some source lane targets it
-          const int row = row_of(i, jx, lane);
-#pragma unroll 1
-          for (unsigned mm = m; mm; mm &= mm - 1) {
-            const int src = __ffs(mm) - 1;
-            const int dst = __shfl_sync(0xffffffffu, pos, src);
-            const float kv = __shfl_sync(0xffffffffu, k, src);
-            const float pv = __shfl_sync(0xffffffffu, v[i], src);
-            const int rv = __shfl_sync(0xffffffffu, row, src);
-            if (lane == dst) { ck = kv; cp = pv; cid = rv; }
+          if (in) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            sk[pos] = (static_cast<unsigned long long>(ord_bits(k)) << 32) | static_cast<unsigned>(row_of(i, jx, lane));
+            sp[pos] = v[i];
           }
           base += __popc(m);
         }
       }
-      warp_sort32(ck, cid, cp, lane);
+      __syncwarp();
+      const unsigned long long mine = sk[lane];
+      const float mypay = sp[lane];
+      int rank = 0;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) rank += (sk[t] < mine) ? 1 : 0;
+      __syncwarp();
       if (!KEYS) {
-        a = __shfl_sync(0xffffffffu, ck, r1 - c_lo);
-        b = __shfl_sync(0xffffffffu, ck, r2 - c_lo);
+        const unsigned ma = __ballot_sync(0xffffffffu, rank == r1 - c_lo);
+        const unsigned mb = __ballot_sync(0xffffffffu, rank == r2 - c_lo);
+        a = __shfl_sync(0xffffffffu, mypay, __ffs(ma) - 1);
+        b = __shfl_sync(0xffffffffu, mypay, __ffs(mb) - 1);
       } else {
         const int take = r1 + 1 - c_lo;             // kept candidates = first `take` in (key,row) order
-        float part = (lane < take) ? cp : 0.f;
-        a = sum_lo + warp_sum(part);
+        a = warp_sum(sum_lo + ((rank < take) ? mypay : 0.f));
       }
       return;
     }
@@ -181,7 +173,7 @@ __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, 
             before += __popc(m);
           }
         }
-        a = sum_lo + warp_sum(part);
+        a = warp_sum(sum_lo + part);
         return;
       }
       p = 0.5f * vmin + 0.5f * vmax;
@@ -223,7 +215,7 @@ __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, 
 template <int S, bool BF16>
 __global__ void __launch_bounds__(kThreads)
 trimmed_mean_kernel(const Params P) {
-  extern __shared__ __align__(16) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots]
+  extern __shared__ __align__(16) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots] + scratch
   constexpr int kGroups = S / 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int es = BF16 ? 2 : 4;
@@ -289,21 +281,21 @@ trimmed_mean_kernel(const Params P) {
 #pragma unroll 1
   for (int cw = warp; cw < kWordCols; cw += kWarps) {
     const int jx = (cw >> 2) & 3;
-    uint32_t wv[S];
+    uint32_t* scratch = tile + kWordCols * kGroups * 128 + warp * 128;   // 512 B of per-warp scratch
     const uint4* t4 = reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane;
-#pragma unroll
-    for (int m = 0; m < kGroups; ++m) {
-      const uint4 t = t4[m * 32];
-      wv[4 * m] = t.x; wv[4 * m + 1] = t.y; wv[4 * m + 2] = t.z; wv[4 * m + 3] = t.w;
-    }
 #pragma unroll 1
     for (int half = 0; half < (BF16 ? 2 : 1); ++half) {
       const int64_t col = col0 + (BF16 ? 2 * cw + half : cw);
       if (col >= P.d) break;                         // warp-uniform
       float x[S];
 #pragma unroll
-      for (int i = 0; i < S; ++i)
-        x[i] = BF16 ? __uint_as_float(half ? (wv[i] & 0xFFFF0000u) : (wv[i] << 16)) : __uint_as_float(wv[i]);
+      for (int m = 0; m < kGroups; ++m) {
+        const uint4 t = t4[m * 32];
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          x[4 * m + q] = BF16 ? __uint_as_float(half ? (w[q] & 0xFFFF0000u) : (w[q] << 16)) : __uint_as_float(w[q]);
+      }
 
       // mean / sigma of the column (pivot model only; never enters the result)
       float s1 = 0.f, s2 = 0.f;
@@ -320,7 +312,7 @@ trimmed_mean_kernel(const Params P) {
 
       // median (np.median: even N -> mean of the two middle order statistics, fp32)
       float a, b;
-      warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, a, b);
+      warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, a, b);
       const float med = ((n & 1) != 0) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
 
       float res;
@@ -330,7 +322,7 @@ trimmed_mean_kernel(const Params P) {
 #pragma unroll
         for (int i = 0; i < S; ++i) x[i] = __fsub_rn(x[i], med);      // devs; padded rows stay +inf
         float total, unused;
-        warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, total, unused);
+        warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, total, unused);
         res = __fadd_rn(__fdiv_rn(total, static_cast<float>(P.keep)), med);
       }
       if (lane == 0) P.out[col] = res;
@@ -366,7 +358,7 @@ static double norm_ppf(double pr) {   // Acklam's rational approximation, |error
 
 template <int S>
 static int launch(const Params& P, int dtype, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(S) * 2048;
+  const size_t smem = static_cast<size_t>(S) * 2048 + kWarps * 512;
   const int cols = dtype == AFL_BF16 ? 32 : 16;
   const unsigned grid = static_cast<unsigned>(ceil_div64(P.d, cols));
   ProfScope ps("trimmed_mean", stream);

@@ -250,11 +250,14 @@ def test_properties_at_scale(api):
     ex = torch.cdist(G[:8, :200000].double(), G[:8, :200000].double()) ** 2
     got = dev.sqdist_partial(G[:8, :200000].contiguous())
     assert float(((got - ex).abs() / ex.clamp_min(1)).max()) < 2e-6
-    # trimmed mean: constant columns, shift equivariance, bounded by the column range
+    # trimmed mean: constant columns, bounded by the column range, parity with the oracle on a column
+    # sample of the big matrix (shift equivariance does NOT hold for this rule: one +T/-T swap at the
+    # keep boundary moves the result by 2T/k, so it is not asserted)
     n2, d2c = 1000, 200_000
     X = torch.randn(n2, d2c, generator=g, device="cuda")
     tm = D.trimmed_mean(X, n2, 240)
     assert bool(((tm >= X.min(0).values) & (tm <= X.max(0).values)).all())
     C = torch.full((n2, 4096), 3.25, device="cuda")
     assert torch.equal(D.trimmed_mean(C, n2, 240), torch.full((4096,), 3.25, device="cuda"))
-    assert float((D.trimmed_mean(X + 2.0, n2, 240) - (tm + 2.0)).abs().max()) < 1e-5
+    cols = torch.arange(0, d2c, 397, device="cuda")
+    close(tm[cols].cpu().numpy(), orc.trimmed_mean(X[:, cols].cpu().numpy(), n2, 240), 0.8)
