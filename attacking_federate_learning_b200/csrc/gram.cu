@@ -45,12 +45,19 @@ struct Params {
   int single_pass;
   int rewrite_hi;
   float* parts;       // [pairs][splits][2][128][128]
+  long long* trace;   // debug: [2 CTAs][kTraceLen][8] clock64 timestamps, or null
 };
+constexpr int kTraceLen = 512;
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // round-to-nearest (ties away) to TF32 precision = cvt.rna.tf32.f32, done on the integer pipe
 __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+__device__ __forceinline__ void trace_ev(const Params& p, int it, int ev) {
+  if (p.trace && it < kTraceLen && (blockIdx.x == 0 || blockIdx.x == 77))
+    p.trace[((blockIdx.x == 0 ? 0 : 1) * kTraceLen + it) * 8 + ev] = clock64();
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -110,7 +117,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   const uint32_t tmem_base = tmem_base_smem;
 
   if (wg == 0) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<64>();
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -118,7 +125,9 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         for (int it = 0; it < nkb; ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
+          trace_ev(p, it, 0);
           mbar_wait(&empty_bar[s], ph ^ 1);
+          trace_ev(p, it, 1);
           uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], has_b ? 2 * kTileBytes : kTileBytes);
           const int col = ((split + (it / kChunk) * p.splits) * kChunk + (it % kChunk)) * kBK;
@@ -143,6 +152,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         mbar_wait(&split_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
+          trace_ev(p, it, 4);
           const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
           const uint64_t da = umma_desc_sw128(st);
           const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
@@ -158,12 +168,13 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           }
           umma_commit(&empty_bar[s]);
           if (in_g == p.flush - 1 || it == nkb - 1) umma_commit(&acc_full[b]);
+          trace_ev(p, it, 5);
         }
         __syncwarp();
       }
     }
   } else if (wg == 1) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<64>();
     // ===================== split warps: lo = RN_tf32(g - hi) =====================
     const int t = threadIdx.x - 128;
     const int nchunks_b = nb * 8;           // 16-byte chunks of the B-side tile (rows < nb)
@@ -171,6 +182,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(&full_bar[s], ph);
+      if (t == 0) trace_ev(p, it, 2);
       uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
       if (!p.single_pass || p.rewrite_hi) {
         float4* src = reinterpret_cast<float4*>(st + (has_b ? off_b : 0));
@@ -206,9 +218,10 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[s]);
+      if (t == 0) trace_ev(p, it, 3);
     }
   } else {
-    setmaxnreg_inc<200>();
+    setmaxnreg_inc<192>();
     // ===================== epilogue: drain TMEM chains into fp32 registers =====================
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int a = (warp - 8) >> 2;      // 0: hi*hi^T accumulator, 1: hi*lo^T accumulator
@@ -220,6 +233,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       const int b = g & 1;
       mbar_wait(&acc_full[b], (g >> 1) & 1);
       tc_fence_after();
+      if (warp == 8 && lane == 0) trace_ev(p, g, 6);
       if (active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>((b * 2 + a) * kTileRows);
@@ -241,6 +255,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
+      if (warp == 8 && lane == 0) trace_ev(p, g, 7);
     }
     float* out = p.parts + (static_cast<size_t>(pair) * p.splits + split) * kPartElems +
                  static_cast<size_t>(a) * kTileRows * kTileRows + static_cast<size_t>(q * 32 + lane) * kTileRows;
@@ -496,9 +511,29 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
       AFL_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
+    const char* trace_path = getenv("AFL_GRAM_TRACE");      // debug aid: dump per-role clock64 timestamps
+    if (trace_path && *trace_path) {
+      AFL_CUDA(cudaMalloc(&p.trace, sizeof(long long) * 2 * kTraceLen * 8));
+      AFL_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * 2 * kTraceLen * 8, stream));
+    }
     {
       ProfScope ps("gram_tcgen05", stream);
       gram_tcgen05_kernel<<<pl.tiles * pl.tiles * pl.splits, kThreads, smem, stream>>>(tmap, p);
+    }
+    if (p.trace) {
+      static long long host_trace[2 * kTraceLen * 8];
+      AFL_CUDA(cudaStreamSynchronize(stream));
+      AFL_CUDA(cudaMemcpy(host_trace, p.trace, sizeof(host_trace), cudaMemcpyDeviceToHost));
+      cudaFree(p.trace);
+      if (FILE* f = fopen(trace_path, "w")) {
+        for (int c = 0; c < 2; ++c)
+          for (int i = 0; i < kTraceLen; ++i) {
+            fprintf(f, "%d %d", c, i);
+            for (int e = 0; e < 8; ++e) fprintf(f, " %lld", host_trace[(c * kTraceLen + i) * 8 + e]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
     }
     AFL_LAUNCH_CHECK("gram_tcgen05_kernel");
     gram_reduce_kernel<<<rgrid, rblock, 0, stream>>>(p.parts, n, pl.tiles, pl.splits, S);

@@ -82,17 +82,18 @@ __device__ __forceinline__ void count_pass(const float (&v)[S], float p, int& c,
   if (KEYS) s = ss;                 // lane-local partial; reduced once at the very end
 }
 
-// Selection over a register-resident column.
+template <int S>
+__device__ __forceinline__ float tie_sum(const float (&v)[S], float T, int need, int jx, int lane);
+
+// Selection over a register-resident column (general path: any data, any bracket state).
 //   KEYS = false : returns the order statistics of ranks r1 <= r2 (r2 <= r1 + 1) in a, b.
 //   KEYS = true  : v holds devs, key = |dev|; r1 == r2 == keep-1; returns in `a` the sum of the `keep`
 //                  devs of smallest key with ties resolved in row order.
 template <int S, bool KEYS>
 __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, int r2, float p0, float density,
-                                            int lane, int jx, uint32_t* scratch, float& a, float& b) {
-  float lo = -kInf, hi = kInf;
-  int c_lo = 0, c_hi = n;
-  float sum_lo = 0.f;
-  bool model = (density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf);
+                                            int lane, int jx, uint32_t* scratch, float lo, float hi, int c_lo, int c_hi,
+                                            float sum_lo, float& a, float& b) {
+  bool model = (density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf) && (lo == -kInf) && (hi == kInf);
   float p = p0;
   a = b = __int_as_float(0x7fc00000);
   for (int iter = 0; iter < 96; ++iter) {
@@ -153,26 +154,7 @@ __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, 
       if (!(vmin < vmax)) {
         // every element of the bracket has the same key (a tie group wider than a warp)
         if (!KEYS) { a = b = vmin; return; }
-        int need = r1 + 1 - c_lo;                    // how many of the tied elements are kept
-        float part = 0.f;
-        int before = 0;
-#pragma unroll
-        for (int g = 0; g < S; g += 4) {
-          unsigned bm[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bm[q] = __ballot_sync(0xffffffffu, fabsf(v[g + q]) == vmin);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {           // true slot order inside the group
-            const int q = kk ^ jx;
-            const unsigned m = q == 0 ? bm[0] : q == 1 ? bm[1] : q == 2 ? bm[2] : bm[3];
-            const float val = q == 0 ? v[g] : q == 1 ? v[g + 1] : q == 2 ? v[g + 2] : v[g + 3];
-            if ((m >> lane) & 1u) {
-              const int rank = before + __popc(m & ((1u << lane) - 1u));
-              if (rank < need) part += val;
-            }
-            before += __popc(m);
-          }
-        }
+        const float part = tie_sum<S>(v, vmin, r1 + 1 - c_lo, jx, lane);
         a = warp_sum(sum_lo + part);
         return;
       }
@@ -212,10 +194,152 @@ __device__ __forceinline__ void warp_select(const float (&v)[S], int n, int r1, 
   }
 }
 
+// Sum, in row order, of the first `need` devs among the elements whose |dev| == T (a tie group that the
+// keep boundary cuts through).  Uses ballots per slot; registers hold each 4-slot group permuted by jx.
+template <int S>
+__device__ __forceinline__ float tie_sum(const float (&v)[S], float T, int need, int jx, int lane) {
+  float part = 0.f;
+  int before = 0;
+#pragma unroll
+  for (int g = 0; g < S; g += 4) {
+    unsigned bm[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bm[q] = __ballot_sync(0xffffffffu, fabsf(v[g + q]) == T);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {           // true slot order inside the group
+      const int q = kk ^ jx;
+      const unsigned m = q == 0 ? bm[0] : q == 1 ? bm[1] : q == 2 ? bm[2] : bm[3];
+      const float val = q == 0 ? v[g] : q == 1 ? v[g + 1] : q == 2 ? v[g + 2] : v[g + 3];
+      if ((m >> lane) & 1u) {
+        const int rank = before + __popc(m & ((1u << lane) - 1u));
+        if (rank < need) part += val;
+      }
+      before += __popc(m);
+    }
+  }
+  return part;
+}
+
+constexpr int kCap = 8;                       // lane-local candidate list capacity (fast path)
+
+// Fast path.  One fused pass over the registers with a model bracket [a, b): counts #{key < a} (and the
+// lane-local dev sum below a), and appends in-bracket elements to a lane-local list in shared memory
+// with predicated stores only (no ballots, no branches; the list wraps instead of overflowing and the
+// wrap is detected from the count).  If the target rank(s) fall inside and <= 32 candidates were
+// collected, they are compacted to one per lane and ranked with 31 shuffles.  Returns false (state
+// updated: lo/c_lo/sum_lo or hi/c_hi tightened where the pass proved a bound) when the general path
+// has to take over.
+template <int S, bool KEYS>
+__device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, int r2, float p0, float density,
+                                            int lane, int jx, uint32_t* scratch, float& lo, float& hi, int& c_lo,
+                                            int& c_hi, float& sum_lo, float& out_a, float& out_b) {
+  if (!((density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf))) return false;
+  float center = p0;
+  float halfw = (11.f + 0.5f * static_cast<float>(r2 - r1)) / density;
+  const uint32_t list_base = smem_u32(scratch) + lane * 4;       // scratch is 1 KB aligned: [kCap][32] words
+#pragma unroll 1
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    float a = center - halfw, b = center + halfw;
+    if (KEYS && a < 0.f) a = 0.f;
+    if (!(a > lo)) a = lo;
+    if (!(b < hi)) b = hi;
+    if (!(a < b)) return false;
+    int ca = 0;
+    float sa = 0.f;
+    uint32_t off = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const float k = keyof<KEYS>(v[i]);
+      const bool below = k < a;
+      ca += below ? 1 : 0;
+      if (KEYS) sa += below ? v[i] : 0.f;
+      const bool in = !below && (k < b);
+      const uint32_t addr = list_base | (off & ((kCap - 1) * 128u));
+      if (in) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(__float_as_uint(v[i])) : "memory");
+        off += 128u;
+      }
+    }
+    const int mine = static_cast<int>(off >> 7);
+    const int c_a = warp_sum_i(ca);
+    const int cin = warp_sum_i(mine);
+    const int cmax = __reduce_max_sync(0xffffffffu, mine);
+    const int c_b = c_a + cin;
+    const bool inside = (c_a <= r1) && (r2 < c_b);
+    if (inside && cin <= 32 && cmax <= kCap) {
+      // ---- dense compaction: exclusive prefix of the per-lane counts, then one candidate per lane
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int excl = incl - mine;
+      __syncwarp();
+      float ent[kCap];
+#pragma unroll
+      for (int k = 0; k < kCap; ++k) ent[k] = __uint_as_float(scratch[k * 32 + lane]);
+      __syncwarp();
+      float* dense = reinterpret_cast<float*>(scratch) + kCap * 32;   // [32] after the lists
+#pragma unroll
+      for (int k = 0; k < kCap; ++k)
+        if (k < mine) dense[excl + k] = ent[k];
+      __syncwarp();
+      const bool have = lane < cin;
+      const float val = have ? dense[lane] : kInf;
+      const float key = have ? keyof<KEYS>(val) : kInf;
+      int lt = 0, le = 0;                       // candidates with key < mine / <= mine (excluding self in lt only)
+#pragma unroll
+      for (int t = 1; t < 32; ++t) {
+        const float ok = __shfl_sync(0xffffffffu, key, (lane + t) & 31);
+        lt += (ok < key) ? 1 : 0;
+        le += (ok <= key) ? 1 : 0;
+      }
+      le += 1;
+      if (!KEYS) {
+        const int t1 = r1 - c_a, t2 = r2 - c_a;
+        const unsigned ma = __ballot_sync(0xffffffffu, have && lt <= t1 && t1 < le);
+        const unsigned mb = __ballot_sync(0xffffffffu, have && lt <= t2 && t2 < le);
+        out_a = __shfl_sync(0xffffffffu, val, __ffs(ma) - 1);
+        out_b = __shfl_sync(0xffffffffu, val, __ffs(mb) - 1);
+        return true;
+      }
+      const int take = r1 + 1 - c_a;            // number of candidates kept, in (key, row) order
+      const unsigned mt = __ballot_sync(0xffffffffu, have && lt < take && take <= le);   // the boundary tie group
+      const int src = __ffs(mt) - 1;
+      const float T = __shfl_sync(0xffffffffu, key, src);
+      const int n_less = __shfl_sync(0xffffffffu, lt, src);
+      const int group = __shfl_sync(0xffffffffu, le, src) - n_less;
+      const int need = take - n_less;
+      float part = sa + ((have && key < T) ? val : 0.f);
+      if (need == group) part += (have && key == T) ? val : 0.f;     // whole tie group kept: order irrelevant
+      else part += tie_sum<S>(v, T, need, jx, lane);                   // boundary cuts the group: row order
+      out_a = warp_sum(part);
+      return true;
+    }
+    // ---- not closed: keep what the pass proved and aim again from the measured counts
+    const float mid = 0.5f * static_cast<float>(r1 + r2) + 0.5f;
+    if (c_a <= r1) { lo = a; c_lo = c_a; sum_lo = sa; } else { hi = a; c_hi = c_a; }
+    if (c_b > r2 && b < hi) { hi = b; c_hi = c_b; }
+    if (inside) {                                   // too many candidates: shrink around the interpolated rank
+      const float w = (b - a) / static_cast<float>(cin > 0 ? cin : 1);
+      center = a + (mid - static_cast<float>(c_a)) * w;
+      halfw = 9.f * w;
+    } else if (c_a > r2) {                          // target below the bracket
+      center = a - (static_cast<float>(c_a) - mid) / density;
+      halfw = (5.f + 0.35f * (static_cast<float>(c_a) - mid)) / density;
+    } else {                                        // target above the bracket
+      center = b + (mid - static_cast<float>(c_b)) / density;
+      halfw = (5.f + 0.35f * (mid - static_cast<float>(c_b))) / density;
+    }
+  }
+  return false;
+}
+
 template <int S, bool BF16>
 __global__ void __launch_bounds__(kThreads)
 trimmed_mean_kernel(const Params P) {
-  extern __shared__ __align__(16) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots] + scratch
+  extern __shared__ __align__(1024) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots] + scratch
   constexpr int kGroups = S / 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int es = BF16 ? 2 : 4;
@@ -225,51 +349,57 @@ trimmed_mean_kernel(const Params P) {
   const uint8_t* base = static_cast<const uint8_t*>(P.G);
 
   // ---------------- staging: coalesced 16-byte row-segment loads -> swizzled smem ----------------
+  // Thread t loads the 16-byte chunk j = t&3 of row (it*64 + t>>2) in iteration `it`.  Row r lives in
+  // slot r>>5 of lane r&31; slot-group m = slot>>2 and the XOR-ed slot position are compile-time
+  // functions of `it`, so every store below has an immediate offset from one of two per-thread bases.
   constexpr int kIters = (32 * S * 4) / kThreads;      // S/2
   constexpr int kBatch = kIters < 4 ? kIters : 4;
-#pragma unroll 1
-  for (int it0 = 0; it0 < kIters; it0 += kBatch) {
-    uint4 val[kBatch];
+  const bool full_tile = P.vec_ok && (col0 + cols_per_tile <= P.d);
+  {
+    const int rowq = tid >> 2, j = tid & 3, l = rowq & 31, hi2 = tid >> 7;
+    uint32_t* b0 = tile + (4 * j * kGroups) * 128 + l * 4 + (hi2 ^ j);
+    uint32_t* b1 = tile + (4 * j * kGroups) * 128 + l * 4 + ((2 + hi2) ^ j);
+    const int64_t c = col0 + static_cast<int64_t>(j) * (16 / es);
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = (it0 + u) * kThreads + tid;
-      const int r = idx >> 2, j = idx & 3;
-      uint4 t = make_uint4(sentinel, sentinel, sentinel, sentinel);
-      if (r < P.n_rows) {
-        int gr = P.row_index ? P.row_index[r] : r;
-        gr = gr < 0 ? gr + P.n_total : gr;
-        const int64_t c = col0 + static_cast<int64_t>(j) * (16 / es);
-        const uint8_t* src = base + (static_cast<int64_t>(gr) * P.ld + c) * es;
-        if (P.vec_ok && c + (16 / es) <= P.d) {
-          t = ldg_stream_u4(reinterpret_cast<const uint4*>(src));
-        } else {
-          uint32_t w[4] = {0u, 0u, 0u, 0u};
-          if (BF16) {
-            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+    for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+      uint4 val[kBatch];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (c + e < P.d) w[e >> 1] |= static_cast<uint32_t>(s16[e]) << ((e & 1) * 16);
+      for (int u = 0; u < kBatch; ++u) {
+        const int r = (it0 + u) * 64 + rowq;
+        uint4 t = make_uint4(sentinel, sentinel, sentinel, sentinel);
+        if (r < P.n_rows) {
+          int gr = P.row_index ? P.row_index[r] : r;
+          gr = gr < 0 ? gr + P.n_total : gr;
+          const uint8_t* src = base + (static_cast<int64_t>(gr) * P.ld + c) * es;
+          if (full_tile) {
+            t = ldg_stream_u4(reinterpret_cast<const uint4*>(src));
           } else {
-            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (BF16) {
+              const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (c + e < P.d) w[e] = s32[e];
+              for (int e = 0; e < 8; ++e)
+                if (c + e < P.d) w[e >> 1] |= static_cast<uint32_t>(s16[e]) << ((e & 1) * 16);
+            } else {
+              const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c + e < P.d) w[e] = s32[e];
+            }
+            t = make_uint4(w[0], w[1], w[2], w[3]);
           }
-          t = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        val[u] = t;
       }
-      val[u] = t;
-    }
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int idx = (it0 + u) * kThreads + tid;
-      const int r = idx >> 2, j = idx & 3;
-      const int slot = r >> 5, l = r & 31, m = slot >> 2, k = slot & 3;
-      const uint32_t w[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int cw = 4 * j + t;
-        tile[((cw * kGroups + m) * 32 + l) * 4 + (k ^ j)] = w[t];
+      for (int u = 0; u < kBatch; ++u) {
+        const int it = it0 + u;
+        uint32_t* b = (it & 1) ? b1 : b0;
+        const int m = it >> 1;
+        b[(0 * kGroups + m) * 128] = val[u].x;
+        b[(1 * kGroups + m) * 128] = val[u].y;
+        b[(2 * kGroups + m) * 128] = val[u].z;
+        b[(3 * kGroups + m) * 128] = val[u].w;
       }
     }
   }
@@ -281,7 +411,7 @@ trimmed_mean_kernel(const Params P) {
 #pragma unroll 1
   for (int cw = warp; cw < kWordCols; cw += kWarps) {
     const int jx = (cw >> 2) & 3;
-    uint32_t* scratch = tile + kWordCols * kGroups * 128 + warp * 128;   // 512 B of per-warp scratch
+    uint32_t* scratch = tile + kWordCols * kGroups * 128 + warp * 512;   // 2 KB of per-warp scratch (1 KB aligned)
     const uint4* t4 = reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane;
 #pragma unroll 1
     for (int half = 0; half < (BF16 ? 2 : 1); ++half) {
@@ -312,7 +442,14 @@ trimmed_mean_kernel(const Params P) {
 
       // median (np.median: even N -> mean of the two middle order statistics, fp32)
       float a, b;
-      warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, a, b);
+      {
+        float lo = -kInf, hi = kInf, sl = 0.f;
+        int c_lo = 0, c_hi = n;
+        if (!select_fast<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
+                                   c_hi, sl, a, b))
+          warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
+                                c_hi, 0.f, a, b);
+      }
       const float med = ((n & 1) != 0) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
 
       float res;
@@ -322,7 +459,12 @@ trimmed_mean_kernel(const Params P) {
 #pragma unroll
         for (int i = 0; i < S; ++i) x[i] = __fsub_rn(x[i], med);      // devs; padded rows stay +inf
         float total, unused;
-        warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, total, unused);
+        float lo = -kInf, hi = kInf, sl = 0.f;
+        int c_lo = 0, c_hi = n;
+        if (!select_fast<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
+                                  c_lo, c_hi, sl, total, unused))
+          warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
+                               c_lo, c_hi, sl, total, unused);
         res = __fadd_rn(__fdiv_rn(total, static_cast<float>(P.keep)), med);
       }
       if (lane == 0) P.out[col] = res;
@@ -358,7 +500,7 @@ static double norm_ppf(double pr) {   // Acklam's rational approximation, |error
 
 template <int S>
 static int launch(const Params& P, int dtype, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(S) * 2048 + kWarps * 512;
+  const size_t smem = static_cast<size_t>(S) * 2048 + kWarps * 2048;
   const int cols = dtype == AFL_BF16 ? 32 : 16;
   const unsigned grid = static_cast<unsigned>(ceil_div64(P.d, cols));
   ProfScope ps("trimmed_mean", stream);

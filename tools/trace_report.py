@@ -1,0 +1,28 @@
+"""Summarise an AFL_GRAM_TRACE dump (clock64 timestamps per role and k-block)."""
+import sys
+import numpy as np
+rows = np.loadtxt(sys.argv[1], dtype=np.int64)
+for cta in (0, 1):
+    t = rows[rows[:, 0] == cta][:, 2:]
+    it = rows[rows[:, 0] == cta][:, 1]
+    ok = t[:, 1] > 0
+    t = t[ok]; n = len(t)
+    if n < 20:
+        continue
+    t0 = t[0, 0]
+    ev = ["prod_wait_start", "tma_issue", "split_start(full)", "split_done", "mma_start", "mma_issued", "epi_start", "epi_done"]
+    print(f"CTA {cta}: {n} k-blocks traced; steady-state per k-block = {(t[n-1,1]-t[20,1])/(n-21):.0f} cycles")
+    sl = slice(24, min(n, 400))
+    print("  tma_issue -> full (TMA latency)      :", np.median(t[sl, 2] - t[sl, 1]))
+    print("  full -> split_done (split work)      :", np.median(t[sl, 3] - t[sl, 2]))
+    print("  split_done -> mma_start (MMA queue)  :", np.median(t[sl, 4] - t[sl, 3]))
+    print("  mma_start -> mma_issued              :", np.median(t[sl, 5] - t[sl, 4]))
+    print("  producer wait for empty              :", np.median(t[sl, 1] - t[sl, 0]))
+    print("  mma_start[i+1]-mma_start[i]          :", np.median(np.diff(t[sl, 4])))
+    print("  tma_issue[i+1]-tma_issue[i]          :", np.median(np.diff(t[sl, 1])))
+    # stage ring depth 6: empty wait of it = mma completion of it-6
+    g = t[:, 6] > 0
+    if g.sum() > 4:
+        print("  epilogue drain (start->done)         :", np.median((t[g, 7] - t[g, 6])[2:]))
+    for i in range(24, 32):
+        print("   it", i, " ".join(f"{int(x - t0):8d}" for x in t[i, :6]))
