@@ -122,38 +122,39 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       // ===================== TMA producer =====================
       if (lane == 0) {
         const uint64_t pol = (p.tiles == 1) ? policy_evict_first() : policy_evict_normal();
+        int s = 0;
+        uint32_t ph = 0;
+        int chunk_col = split * kChunk * kBK, in_chunk = 0;
         for (int it = 0; it < nkb; ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
           trace_ev(p, it, 0);
           mbar_wait(&empty_bar[s], ph ^ 1);
           trace_ev(p, it, 1);
           uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], has_b ? 2 * kTileBytes : kTileBytes);
-          const int col = ((split + (it / kChunk) * p.splits) * kChunk + (it % kChunk)) * kBK;
+          const int col = chunk_col + in_chunk * kBK;
           tma_load_2d(st, &tmap, &full_bar[s], col, ti * kTileRows, pol);
           if (has_b) tma_load_2d(st + off_b, &tmap, &full_bar[s], col, tj * kTileRows, pol);
+          if (++in_chunk == kChunk) { in_chunk = 0; chunk_col += p.splits * kChunk * kBK; }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     } else if (warp == 1) {
       // ===================== MMA issuer (one thread) =====================
       const uint32_t idesc = umma_idesc_tf32(kTileRows, nb);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        const int g = it / p.flush;
-        const int in_g = it - g * p.flush;
-        const int b = g & 1;
-        if (in_g == 0) {
-          mbar_wait(&acc_empty[b], ((g >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        int s = 0, in_g = 0, g = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < nkb; ++it) {
+          const int b = g & 1;
+          if (in_g == 0) {
+            mbar_wait(&acc_empty[b], ((g >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&split_bar[s], ph);
           tc_fence_after();
-        }
-        mbar_wait(&full_bar[s], ph);
-        mbar_wait(&split_bar[s], ph);
-        tc_fence_after();
-        if (lane == 0) {
           trace_ev(p, it, 4);
-          const uint32_t st = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+          const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
           const uint64_t da = umma_desc_sw128(st);
           const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
           const uint64_t dl = umma_desc_sw128(st + off_lo);
@@ -167,10 +168,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             if (!p.single_pass) umma_tf32(d_x, da + adv, dl + adv, idesc, acc);
           }
           umma_commit(&empty_bar[s]);
-          if (in_g == p.flush - 1 || it == nkb - 1) umma_commit(&acc_full[b]);
+          const bool last_in_group = (in_g == p.flush - 1) || (it == nkb - 1);
+          if (last_in_group) umma_commit(&acc_full[b]);
           trace_ev(p, it, 5);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+          if (last_in_group) { in_g = 0; ++g; } else { ++in_g; }
         }
-        __syncwarp();
       }
     }
   } else if (wg == 1) {
@@ -178,10 +181,10 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     // ===================== split warps: lo = RN_tf32(g - hi) =====================
     const int t = threadIdx.x - 128;
     const int nchunks_b = nb * 8;           // 16-byte chunks of the B-side tile (rows < nb)
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < nkb; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(&full_bar[s], ph);
+      mbar_wait_warp(&full_bar[s], ph);
       if (t == 0) trace_ev(p, it, 2);
       uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
       if (!p.single_pass || p.rewrite_hi) {
@@ -219,6 +222,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[s]);
       if (t == 0) trace_ev(p, it, 3);
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else {
     setmaxnreg_inc<192>();
@@ -231,7 +235,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const bool active = !(a == 1 && p.single_pass);
     for (int g = 0; g < ngroups; ++g) {
       const int b = g & 1;
-      mbar_wait(&acc_full[b], (g >> 1) & 1);
+      mbar_wait_warp(&acc_full[b], (g >> 1) & 1);
       tc_fence_after();
       if (warp == 8 && lane == 0) trace_ev(p, g, 6);
       if (active) {

@@ -236,7 +236,7 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
   if (!((density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf))) return false;
   float center = p0;
   float halfw = (11.f + 0.5f * static_cast<float>(r2 - r1)) / density;
-  const uint32_t list_base = smem_u32(scratch) + lane * 4;       // scratch is 1 KB aligned: [kCap][32] words
+  const uint32_t list_base = smem_u32(scratch) + lane * 4;       // lists: [kCap][32] words
 #pragma unroll 1
   for (int attempt = 0; attempt < 3; ++attempt) {
     float a = center - halfw, b = center + halfw;
@@ -254,7 +254,7 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
       ca += below ? 1 : 0;
       if (KEYS) sa += below ? v[i] : 0.f;
       const bool in = !below && (k < b);
-      const uint32_t addr = list_base | (off & ((kCap - 1) * 128u));
+      const uint32_t addr = list_base + (off & ((kCap - 1) * 128u));   // wraps instead of overflowing
       if (in) {
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(__float_as_uint(v[i])) : "memory");
         off += 128u;
