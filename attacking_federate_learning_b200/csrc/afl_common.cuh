@@ -114,7 +114,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
+    if (++spins > (1u << 21)) {
       printf("afl: mbarrier timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, (void*)bar, parity);
       __trap();
@@ -127,7 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
   __syncwarp();
-  while (!mbar_try_wait(bar, parity)) {}
+  mbar_wait(bar, parity);          // completes on the first probe; bounded like every other wait
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)

@@ -45,9 +45,10 @@ struct Params {
   int single_pass;
   int rewrite_hi;
   float* parts;       // [pairs][splits][2][128][128]
-  long long* trace;   // debug: [2 CTAs][kTraceLen][8] clock64 timestamps, or null
+  long long* trace;   // debug: [2 CTAs][kTraceLen][kTraceEv] clock64 timestamps, or null
 };
 constexpr int kTraceLen = 512;
+constexpr int kTraceEv = 12;
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // round-to-nearest (ties away) to TF32 precision = cvt.rna.tf32.f32, done on the integer pipe
@@ -57,7 +58,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 __device__ __forceinline__ void trace_ev(const Params& p, int it, int ev) {
   if (p.trace && it < kTraceLen && (blockIdx.x == 0 || blockIdx.x == 77))
-    p.trace[((blockIdx.x == 0 ? 0 : 1) * kTraceLen + it) * 8 + ev] = clock64();
+    p.trace[((blockIdx.x == 0 ? 0 : 1) * kTraceLen + it) * kTraceEv + ev] = clock64();
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -194,6 +195,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)                       // all loads first: 8 LDS.128 in flight per thread
           if (t + u * 128 < nchunks_b) v[u] = src[t + u * 128];
+        if (t == 0) trace_ev(p, it, 8);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (t + u * 128 < nchunks_b) {
@@ -217,7 +219,9 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             a[c] = v;
           }
         }
+        if (t == 0) trace_ev(p, it, 9);
         fence_proxy_async_smem();
+        if (t == 0) trace_ev(p, it, 10);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[s]);
@@ -517,15 +521,15 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     }
     const char* trace_path = getenv("AFL_GRAM_TRACE");      // debug aid: dump per-role clock64 timestamps
     if (trace_path && *trace_path) {
-      AFL_CUDA(cudaMalloc(&p.trace, sizeof(long long) * 2 * kTraceLen * 8));
-      AFL_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * 2 * kTraceLen * 8, stream));
+      AFL_CUDA(cudaMalloc(&p.trace, sizeof(long long) * 2 * kTraceLen * kTraceEv));
+      AFL_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * 2 * kTraceLen * kTraceEv, stream));
     }
     {
       ProfScope ps("gram_tcgen05", stream);
       gram_tcgen05_kernel<<<pl.tiles * pl.tiles * pl.splits, kThreads, smem, stream>>>(tmap, p);
     }
     if (p.trace) {
-      static long long host_trace[2 * kTraceLen * 8];
+      static long long host_trace[2 * kTraceLen * kTraceEv];
       AFL_CUDA(cudaStreamSynchronize(stream));
       AFL_CUDA(cudaMemcpy(host_trace, p.trace, sizeof(host_trace), cudaMemcpyDeviceToHost));
       cudaFree(p.trace);
@@ -533,7 +537,7 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
         for (int c = 0; c < 2; ++c)
           for (int i = 0; i < kTraceLen; ++i) {
             fprintf(f, "%d %d", c, i);
-            for (int e = 0; e < 8; ++e) fprintf(f, " %lld", host_trace[(c * kTraceLen + i) * 8 + e]);
+            for (int e = 0; e < kTraceEv; ++e) fprintf(f, " %lld", host_trace[(c * kTraceLen + i) * kTraceEv + e]);
             fprintf(f, "\n");
           }
         fclose(f);

@@ -285,7 +285,7 @@ def main():
         e = dict(os.environ); e.update(env)
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, __file__, "case", name], env=e, capture_output=True, text=True, timeout=600)
+            p = subprocess.run([sys.executable, __file__, "case", name], env=e, capture_output=True, text=True, timeout=int(os.environ.get('DIAG_CASE_TIMEOUT', '150')))
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             rec = {"case": name, "rc": p.returncode, "s": round(time.time() - t0, 1)}
             if line:

@@ -15,6 +15,11 @@ for cta in (0, 1):
     sl = slice(24, min(n, 400))
     print("  tma_issue -> full (TMA latency)      :", np.median(t[sl, 2] - t[sl, 1]))
     print("  full -> split_done (split work)      :", np.median(t[sl, 3] - t[sl, 2]))
+    if t.shape[1] > 10:
+        print("    split: start->loads issued         :", np.median(t[sl, 8] - t[sl, 2]))
+        print("    split: loads->stores issued        :", np.median(t[sl, 9] - t[sl, 8]))
+        print("    split: fence.proxy.async           :", np.median(t[sl, 10] - t[sl, 9]))
+        print("    split: fence->arrive               :", np.median(t[sl, 3] - t[sl, 10]))
     print("  split_done -> mma_start (MMA queue)  :", np.median(t[sl, 4] - t[sl, 3]))
     print("  mma_start -> mma_issued              :", np.median(t[sl, 5] - t[sl, 4]))
     print("  producer wait for empty              :", np.median(t[sl, 1] - t[sl, 0]))
@@ -24,5 +29,3 @@ for cta in (0, 1):
     g = t[:, 6] > 0
     if g.sum() > 4:
         print("  epilogue drain (start->done)         :", np.median((t[g, 7] - t[g, 6])[2:]))
-    for i in range(24, 32):
-        print("   it", i, " ".join(f"{int(x - t0):8d}" for x in t[i, :6]))
