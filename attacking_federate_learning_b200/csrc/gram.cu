@@ -188,35 +188,21 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       mbar_wait_warp(&full_bar[s], ph);
       if (t == 0) trace_ev(p, it, 2);
       uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
-      if (!p.single_pass || p.rewrite_hi) {
-        float4* src = reinterpret_cast<float4*>(st + (has_b ? off_b : 0));
-        float4* dst = reinterpret_cast<float4*>(st + off_lo);
+      if (!p.single_pass) {
+        const uint32_t src = smem_u32(st + (has_b ? off_b : 0)) + static_cast<uint32_t>(t) * 16u;
+        const uint32_t dst = smem_u32(st + off_lo) + static_cast<uint32_t>(t) * 16u;
         float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)                       // all loads first: 8 LDS.128 in flight per thread
-          if (t + u * 128 < nchunks_b) v[u] = src[t + u * 128];
+        for (int u = 0; u < 8; ++u)                       // all loads first: up to 8 LDS.128 in flight per thread
+          if (t + u * 128 < nchunks_b) v[u] = lds128(src + u * 2048);
         if (t == 0) trace_ev(p, it, 8);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (t + u * 128 < nchunks_b) {
-            float4 h, l;
-            if (p.rewrite_hi) {
-              h.x = tf32_rna(v[u].x); h.y = tf32_rna(v[u].y); h.z = tf32_rna(v[u].z); h.w = tf32_rna(v[u].w);
-              src[t + u * 128] = h;
-            } else {
-              h.x = tf32_trunc(v[u].x); h.y = tf32_trunc(v[u].y); h.z = tf32_trunc(v[u].z); h.w = tf32_trunc(v[u].w);
-            }
-            l.x = tf32_rna(v[u].x - h.x); l.y = tf32_rna(v[u].y - h.y);
-            l.z = tf32_rna(v[u].z - h.z); l.w = tf32_rna(v[u].w - h.w);
-            dst[t + u * 128] = l;
-          }
-        }
-        if (p.rewrite_hi && has_b) {  // A-side tile is a different row block: round it too
-          float4* a = reinterpret_cast<float4*>(st);
-          for (int c = t; c < kTileRows * 8; c += 128) {
-            float4 v = a[c];
-            v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
-            a[c] = v;
+            float4 l;                                     // hi = what the tensor core keeps of an fp32 operand
+            l.x = tf32_rna(v[u].x - tf32_trunc(v[u].x)); l.y = tf32_rna(v[u].y - tf32_trunc(v[u].y));
+            l.z = tf32_rna(v[u].z - tf32_trunc(v[u].z)); l.w = tf32_rna(v[u].w - tf32_trunc(v[u].w));
+            sts128(dst + u * 2048, l);
           }
         }
         if (t == 0) trace_ev(p, it, 9);
@@ -510,7 +496,7 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     p.n = n; p.tiles = pl.tiles; p.splits = pl.splits; p.kblocks = static_cast<int>((d + kBK - 1) / kBK);
     p.flush = pl.flush; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
     p.single_pass = (flags & AFL_GRAM_SINGLE_PASS) ? 1 : 0;
-    p.rewrite_hi = (flags & AFL_GRAM_REWRITE_HI) ? 1 : 0;
+    p.rewrite_hi = 0;   // AFL_GRAM_REWRITE_HI is accepted but ignored: kind::tf32 was measured to truncate
     p.parts = static_cast<float*>(ws);
     double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
     const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024;

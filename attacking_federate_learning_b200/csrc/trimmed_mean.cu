@@ -317,7 +317,19 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
       out_a = warp_sum(part);
       return true;
     }
-    // ---- not closed: keep what the pass proved and aim again from the measured counts
+    if (!KEYS && c_a > r1 && c_a <= r2) {
+      // the lower pivot separates the two middle order statistics (even N): read them off directly
+      float below = -kInf, above = kInf;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        below = (v[i] < a) ? fmaxf(below, v[i]) : below;
+        above = (v[i] >= a) ? fminf(above, v[i]) : above;
+      }
+      out_a = warp_max_f(below);
+      out_b = warp_min_f(above);
+      return true;
+    }
+    // ---- not closed: keep what the pass proved (invariants: c_lo <= r1, r2 < c_hi) and aim again
     const float mid = 0.5f * static_cast<float>(r1 + r2) + 0.5f;
     if (c_a <= r1) { lo = a; c_lo = c_a; sum_lo = sa; } else { hi = a; c_hi = c_a; }
     if (c_b > r2 && b < hi) { hi = b; c_hi = c_b; }

@@ -53,8 +53,8 @@ enum {
   AFL_GRAM_FORCE_SIMT = 1,    /* CUDA-core difference kernel (verification / unaligned pitch)      */
   AFL_GRAM_FORCE_TCGEN05 = 2, /* fail with AFL_ERR_UNSUPPORTED instead of falling back to SIMT     */
   AFL_GRAM_SINGLE_PASS = 4,   /* tcgen05: hi*hi only (plain TF32), for measurement                  */
-  AFL_GRAM_REWRITE_HI = 8     /* tcgen05: store RN(tf32) hi parts back to smem instead of relying   */
-                              /*          on the tensor core ignoring the low 13 mantissa bits      */
+  AFL_GRAM_REWRITE_HI = 8     /* accepted, ignored (kind::tf32 was measured to ignore the low 13     */
+                              /* mantissa bits of fp32 operands, which is what the split relies on)  */
 };
 
 /* ---- library / device ------------------------------------------------------------------------ */
