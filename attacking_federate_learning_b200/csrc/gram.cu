@@ -93,7 +93,9 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     nkb -= nchunks_total * kChunk - p.kblocks;          // the globally last chunk may be short
   const int ngroups = (nkb + p.flush - 1) / p.flush;
   const uint32_t off_b = kTileBytes;
-  const uint32_t off_lo = (p.stage_bytes == 3 * kTileBytes) ? 2 * kTileBytes : kTileBytes;
+  // lo tile sits directly behind the nb valid rows of the B-side tile, so that raw||lo is ONE K-major
+  // operand of 2*nb rows (rows nb..127 of that tile are TMA zero fill and may be overwritten)
+  const uint32_t off_lo = (has_b ? off_b : 0u) + static_cast<uint32_t>(nb) * 128u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -141,40 +143,38 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
     } else if (warp == 1) {
       // ===================== MMA issuer (one thread) =====================
-      const uint32_t idesc = umma_idesc_tf32(kTileRows, nb);
-      if (lane == 0) {
-        int s = 0, in_g = 0, g = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < nkb; ++it) {
-          const int b = g & 1;
-          if (in_g == 0) {
-            mbar_wait(&acc_empty[b], ((g >> 1) & 1) ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(&full_bar[s], ph);
-          mbar_wait(&split_bar[s], ph);
+      // The whole warp runs this loop convergently; one elected lane issues.  (Issuing from inside a
+      // divergent `if (lane == 0)` makes the compiler wrap every UTCHMMA in an ELECT/retry loop.)
+      const uint32_t idesc = umma_idesc_tf32(kTileRows, p.single_pass ? nb : 2 * nb);
+      int s = 0, in_g = 0, g = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < nkb; ++it) {
+        const int b = g & 1;
+        if (in_g == 0) {
+          mbar_wait_warp(&acc_empty[b], ((g >> 1) & 1) ^ 1);
           tc_fence_after();
+        }
+        mbar_wait_warp(&split_bar[s], ph);              // implies the TMA data of this stage has landed
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
+        const uint64_t da = umma_desc_sw128(st);
+        const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
+        const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
+        const bool last_in_group = (in_g == p.flush - 1) || (it == nkb - 1);
+        if (elect_one()) {
           trace_ev(p, it, 4);
-          const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
-          const uint64_t da = umma_desc_sw128(st);
-          const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
-          const uint64_t dl = umma_desc_sw128(st + off_lo);
-          const uint32_t d_hh = tmem_base + static_cast<uint32_t>((b * 2 + 0) * kTileRows);
-          const uint32_t d_x = tmem_base + static_cast<uint32_t>((b * 2 + 1) * kTileRows);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t acc = (in_g | ks) != 0;
             const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 32 bytes (8 tf32) >> 4
-            umma_tf32(d_hh, da + adv, db + adv, idesc, acc);
-            if (!p.single_pass) umma_tf32(d_x, da + adv, dl + adv, idesc, acc);
+            umma_tf32(d_acc, da + adv, db + adv, idesc, (in_g | ks) != 0);   // [hi*hi^T | hi*lo^T], N = 2*nb
           }
           umma_commit(&empty_bar[s]);
-          const bool last_in_group = (in_g == p.flush - 1) || (it == nkb - 1);
           if (last_in_group) umma_commit(&acc_full[b]);
           trace_ev(p, it, 5);
-          if (++s == p.stages) { s = 0; ph ^= 1; }
-          if (last_in_group) { in_g = 0; ++g; } else { ++in_g; }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (last_in_group) { in_g = 0; ++g; } else { ++in_g; }
       }
     }
   } else if (wg == 1) {
@@ -230,7 +230,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       if (warp == 8 && lane == 0) trace_ev(p, g, 6);
       if (active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>((b * 2 + a) * kTileRows);
+                               static_cast<uint32_t>(b * 256 + a * nb);
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
           if (c * 16 < nb) {
