@@ -31,6 +31,9 @@ constexpr int kTileRows = 128;               // UMMA M, and the largest UMMA N u
 constexpr int kTileBytes = kTileRows * 128;  // 16 KB
 constexpr int kThreads = 512;                // 4 warpgroups
 constexpr int kTmemCols = 512;
+#ifndef AFL_SPLIT_RN
+#define AFL_SPLIT_RN 0
+#endif
 constexpr int kChunk = 4;                    // k-blocks per contiguous K chunk (4 x 128 B = 512 B per row)
 constexpr int kPartElems = 2 * kTileRows * kTileRows;  // per (pair, split): [2][128][128] fp32
 
@@ -48,7 +51,7 @@ struct Params {
   long long* trace;   // debug: [2 CTAs][kTraceLen][kTraceEv] clock64 timestamps, or null
 };
 constexpr int kTraceLen = 512;
-constexpr int kTraceEv = 12;
+constexpr int kTraceEv = 16;
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // round-to-nearest (ties away) to TF32 precision = cvt.rna.tf32.f32, done on the integer pipe
@@ -68,7 +71,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   // contract, so align by hand (the host adds 1 KB of slack).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], split_bar[8], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2], first_issued[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -101,11 +104,11 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&split_bar[s], 4);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_full[b], 2);        // one tcgen05.commit from each of the two MMA issuer warps
       mbar_init(&acc_empty[b], 8);
+      mbar_init(&first_issued[b], 1);
     }
     fence_mbar_init();
   }
@@ -141,40 +144,54 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer (one thread) =====================
-      // The whole warp runs this loop convergently; one elected lane issues.  (Issuing from inside a
-      // divergent `if (lane == 0)` makes the compiler wrap every UTCHMMA in an ELECT/retry loop.)
+    } else if (warp == 1 || warp == 3) {
+      // ===================== MMA issuers: two warps, alternating k-blocks =====================
+      // An issuing thread is blocked while its UTCHMMAs drain into the tensor queue (~one k-block of
+      // tensor time) and then needs several hundred cycles of barrier latency before it can issue
+      // again; with two issuers one waits while the other issues.  Each warp runs its loop
+      // convergently and one elected lane issues (issuing from a divergent `if (lane == 0)` makes
+      // the compiler wrap every UTCHMMA in an ELECT/retry loop).  Both issuers accumulate into the
+      // same TMEM buffer; the overwrite (accumulate = 0) MMA of a group is always issuer 0's first,
+      // and issuer 1 does not start a group before that MMA has been issued (`first_issued`).
+      const int j = (warp == 3) ? 1 : 0;
       const uint32_t idesc = umma_idesc_tf32(kTileRows, p.single_pass ? nb : 2 * nb);
-      int s = 0, in_g = 0, g = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < nkb; ++it) {
+      int s = j;
+      for (int g = 0; g < ngroups; ++g) {
         const int b = g & 1;
-        if (in_g == 0) {
-          mbar_wait_warp(&acc_empty[b], ((g >> 1) & 1) ^ 1);
+        const uint32_t gph = (g >> 1) & 1;
+        const int it_begin = g * p.flush, it_end = min(it_begin + p.flush, nkb);
+        const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
+        int it = it_begin + j;                          // flush is even: parity of `it` == issuer id
+        if (it < it_end) {
+          mbar_wait_warp(&acc_empty[b], gph ^ 1);
+          if (j == 1) mbar_wait_warp(&first_issued[b], gph);
           tc_fence_after();
         }
-        mbar_wait_warp(&split_bar[s], ph);              // implies the TMA data of this stage has landed
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
-        const uint64_t da = umma_desc_sw128(st);
-        const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
-        const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
-        const bool last_in_group = (in_g == p.flush - 1) || (it == nkb - 1);
-        if (elect_one()) {
-          trace_ev(p, it, 4);
+        for (; it < it_end; it += 2) {
+          if (lane == 0) trace_ev(p, it, 11);
+          named_bar_sync(1 + s, 128 + 32);              // split warps have produced stage s (implies TMA landed)
+          if (lane == 0) trace_ev(p, it, 12);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
+          const uint64_t da = umma_desc_sw128(st);
+          const uint64_t db = umma_desc_sw128(st + (has_b ? off_b : 0));
+          if (elect_one()) {
+            trace_ev(p, it, 4);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 32 bytes (8 tf32) >> 4
-            umma_tf32(d_acc, da + adv, db + adv, idesc, (in_g | ks) != 0);   // [hi*hi^T | hi*lo^T], N = 2*nb
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 32 bytes (8 tf32) >> 4
+              umma_tf32(d_acc, da + adv, db + adv, idesc, (it != it_begin) || (ks != 0));   // [hi*hi^T | hi*lo^T]
+            }
+            umma_commit(&empty_bar[s]);
+            if (it == it_begin) mbar_arrive(&first_issued[b]);
+            trace_ev(p, it, 5);
           }
-          umma_commit(&empty_bar[s]);
-          if (last_in_group) umma_commit(&acc_full[b]);
-          trace_ev(p, it, 5);
+          __syncwarp();
+          s += 2;
+          if (s >= p.stages) s -= p.stages;
         }
+        if (elect_one()) umma_commit(&acc_full[b]);     // arrives once this issuer's MMAs of the group are done
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-        if (last_in_group) { in_g = 0; ++g; } else { ++in_g; }
       }
     }
   } else if (wg == 1) {
@@ -200,8 +217,13 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         for (int u = 0; u < 8; ++u) {
           if (t + u * 128 < nchunks_b) {
             float4 l;                                     // hi = what the tensor core keeps of an fp32 operand
+#if AFL_SPLIT_RN
             l.x = tf32_rna(v[u].x - tf32_trunc(v[u].x)); l.y = tf32_rna(v[u].y - tf32_trunc(v[u].y));
             l.z = tf32_rna(v[u].z - tf32_trunc(v[u].z)); l.w = tf32_rna(v[u].w - tf32_trunc(v[u].w));
+#else                                                     // exact residual; the tensor core truncates it to 11 bits
+            l.x = v[u].x - tf32_trunc(v[u].x); l.y = v[u].y - tf32_trunc(v[u].y);
+            l.z = v[u].z - tf32_trunc(v[u].z); l.w = v[u].w - tf32_trunc(v[u].w);
+#endif
             sts128(dst + u * 2048, l);
           }
         }
@@ -209,8 +231,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         fence_proxy_async_smem();
         if (t == 0) trace_ev(p, it, 10);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&split_bar[s]);
+      named_bar_arrive(1 + s, 128 + 32);
       if (t == 0) trace_ev(p, it, 3);
       if (++s == p.stages) { s = 0; ph ^= 1; }
     }
@@ -442,7 +463,8 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     pl.stage_bytes = (pl.tiles == 1) ? 2 * kTileBytes : 3 * kTileBytes;
     pl.stages = (pl.tiles == 1) ? 6 : 4;
     pl.flush = env_int("AFL_GRAM_FLUSH", 4);
-    if (pl.flush < 1) pl.flush = 1;
+    if (pl.flush < 2) pl.flush = 2;
+    pl.flush &= ~1;                                     // even: the two issuers alternate k-blocks
     pl.parts_bytes = static_cast<size_t>(pairs) * pl.splits * kPartElems * sizeof(float);
     pl.s_bytes = align_up(static_cast<size_t>(n) * n * sizeof(double), 256);
     pl.total = pl.parts_bytes + pl.s_bytes;

@@ -22,6 +22,11 @@ for cta in (0, 1):
         print("    split: fence->arrive               :", np.median(t[sl, 3] - t[sl, 10]))
     print("  split_done -> mma_start (MMA queue)  :", np.median(t[sl, 4] - t[sl, 3]))
     print("  mma_start -> mma_issued              :", np.median(t[sl, 5] - t[sl, 4]))
+    if t.shape[1] > 13:
+        print("    mma loop: issued(i-1) -> loop top(i) :", np.median(t[sl, 11][1:] - t[sl, 5][:-1]))
+        print("    mma loop: wait split_bar            :", np.median(t[sl, 12] - t[sl, 11]))
+        print("    mma loop: tcgen05.fence::after      :", np.median(t[sl, 13] - t[sl, 12]))
+        print("    mma loop: fence -> elected          :", np.median(t[sl, 4] - t[sl, 13]))
     print("  producer wait for empty              :", np.median(t[sl, 1] - t[sl, 0]))
     print("  mma_start[i+1]-mma_start[i]          :", np.median(np.diff(t[sl, 4])))
     print("  tma_issue[i+1]-tma_issue[i]          :", np.median(np.diff(t[sl, 1])))
