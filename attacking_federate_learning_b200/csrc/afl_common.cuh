@@ -142,10 +142,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
 }
 
 // Named barriers (ids 1..15; 0 is __syncthreads): producers bar.arrive, the consumer warp bar.sync.
+// (aligned barriers: the whole warp must execute them convergently, hence the __syncwarp)
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  __syncwarp();
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  __syncwarp();
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
@@ -179,6 +182,15 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS), zero-filling bytes past src_bytes, and an
+// mbarrier arrival that fires when all of this thread's earlier cp.async have landed.
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

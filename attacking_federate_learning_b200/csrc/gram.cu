@@ -48,6 +48,10 @@ struct Params {
   int single_pass;
   int rewrite_hi;
   float* parts;       // [pairs][splits][2][128][128]
+  int box_rows;       // rows per TMA box (<= 128; rows past it are never written and only feed ignored outputs)
+  int loader;         // 0: TMA boxes, 1: cp.async (LDGSTS) rows written in the same swizzled layout
+  const float* G;     // matrix base and pitch (elements) for the cp.async loader
+  int64_t ld, d;
   long long* trace;   // debug: [2 CTAs][kTraceLen][kTraceEv] clock64 timestamps, or null
 };
 constexpr int kTraceLen = 512;
@@ -102,7 +106,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], p.loader ? 32 : 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -124,8 +128,40 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 
   if (wg == 0) {
     setmaxnreg_dec<64>();
-    if (warp == 0) {
+    if (p.loader == 1 && (warp == 0 || warp == 2)) {
+      // ===================== cp.async producers: two warps, alternating stages =====================
+      // Lane l copies 16-byte chunk (l & 7) of row 4*i + (l >> 3); the destination is the position a TMA
+      // box with SWIZZLE_128B would have used: row*128 + ((chunk ^ (row & 7)) << 4).
+      const int j = (warp == 2) ? 1 : 0;
+      const int rows_i = min(kTileRows, p.n - ti * kTileRows);
+      const int sub = lane >> 3, c16 = lane & 7;
+      int s = j;
+      uint32_t ph = 0;
+      for (int it = j; it < nkb; it += 2) {
+        mbar_wait_warp(&empty_bar[s], ph ^ 1);
+        if (lane == 0) trace_ev(p, it, 1);
+        const int col = ((split + (it / kChunk) * p.splits) * kChunk + (it % kChunk)) * kBK + c16 * 4;
+        const int64_t remain = p.d - col;
+        const uint32_t nbytes = remain >= 4 ? 16u : (remain > 0 ? static_cast<uint32_t>(remain) * 4u : 0u);
+        const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
+        const float* gcol = p.G + (remain > 0 ? col : 0);
+#pragma unroll 5
+        for (int r = sub; r < rows_i; r += 4)
+          cp_async_16(st + r * 128 + ((c16 ^ (r & 7)) << 4), gcol + static_cast<int64_t>(ti * kTileRows + r) * p.ld, nbytes);
+        if (has_b) {
+#pragma unroll 5
+          for (int r = sub; r < rows_j; r += 4)
+            cp_async_16(st + off_b + r * 128 + ((c16 ^ (r & 7)) << 4),
+                        gcol + static_cast<int64_t>(tj * kTileRows + r) * p.ld, nbytes);
+        }
+        cp_async_mbar_arrive_noinc(&full_bar[s]);
+        s += 2;
+        if (s >= p.stages) { s -= p.stages; ph ^= 1; }
+      }
+    } else if (warp == 0) {
       // ===================== TMA producer =====================
+      if (p.loader == 1) {
+      } else
       if (lane == 0) {
         const uint64_t pol = (p.tiles == 1) ? policy_evict_first() : policy_evict_normal();
         int s = 0;
@@ -136,7 +172,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           trace_ev(p, it, 1);
           uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[s], has_b ? 2 * kTileBytes : kTileBytes);
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(p.box_rows) * 128u * (has_b ? 2u : 1u));
           const int col = chunk_col + in_chunk * kBK;
           tma_load_2d(st, &tmap, &full_bar[s], col, ti * kTileRows, pol);
           if (has_b) tma_load_2d(st + off_b, &tmap, &full_bar[s], col, tj * kTileRows, pol);
@@ -231,6 +267,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         fence_proxy_async_smem();
         if (t == 0) trace_ev(p, it, 10);
       }
+      if (p.single_pass && p.loader == 1) fence_proxy_async_smem();   // cp.async data -> async proxy
       named_bar_arrive(1 + s, 128 + 32);
       if (t == 0) trace_ev(p, it, 3);
       if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -508,7 +545,9 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
-    const cuuint32_t box[2] = {kBK, kTileRows};
+    int box_rows = env_int("AFL_GRAM_BOXROWS", kTileRows);
+    if (box_rows < 8 || box_rows > kTileRows || pl.tiles > 1) box_rows = kTileRows;
+    const cuuint32_t box[2] = {kBK, static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t estride[2] = {1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(G), gdim, gstride, box, estride,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -518,6 +557,9 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     p.n = n; p.tiles = pl.tiles; p.splits = pl.splits; p.kblocks = static_cast<int>((d + kBK - 1) / kBK);
     p.flush = pl.flush; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
     p.single_pass = (flags & AFL_GRAM_SINGLE_PASS) ? 1 : 0;
+    p.box_rows = box_rows;
+    p.loader = env_int("AFL_GRAM_LOADER", 0) ? 1 : 0;
+    p.G = static_cast<const float*>(G); p.ld = ld; p.d = d;
     p.rewrite_hi = 0;   // AFL_GRAM_REWRITE_HI is accepted but ignored: kind::tf32 was measured to truncate
     p.parts = static_cast<float*>(ws);
     double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);

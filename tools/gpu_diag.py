@@ -252,6 +252,12 @@ reg("c2_gram", case_gram, 100, 11_200_000, F["TC"], "c2", True)
 reg("c2_gram_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], "c2_single", True)
 reg("c2_gram_flush2", case_gram, 100, 11_200_000, F["TC"], "c2", True, env={"AFL_GRAM_FLUSH": "2"})
 reg("c2_gram_flush32", case_gram, 100, 11_200_000, F["TC"], "c2", True, env={"AFL_GRAM_FLUSH": "32"})
+reg("c2_cpasync", case_gram, 100, 11_200_000, F["TC"], "c2_cpasync", True, env={"AFL_GRAM_LOADER": "1"})
+reg("c2_cpasync_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], "c2_cpasync_single", True, env={"AFL_GRAM_LOADER": "1"})
+reg("c2_box104", case_gram, 100, 11_200_000, F["TC"], "c2_box104", True, env={"AFL_GRAM_BOXROWS": "104"})
+reg("c2_box104_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], "c2_box104_single", True, env={"AFL_GRAM_BOXROWS": "104"})
+reg("ident_cpasync", case_gram_identical, 40, 5000, F["TC"], env={"AFL_GRAM_LOADER": "1"})
+reg("n200_cpasync", case_gram, 200, 4096, F["TC"], "tc", env={"AFL_GRAM_LOADER": "1"})
 reg("n500_gram", case_gram, 500, 1 << 20, F["TC"], "n500", True)
 reg("n1000_gram", case_gram, 1000, 1 << 19, F["TC"], "n1000", True)
 reg("select_10", case_select, 10, 2, 0)
