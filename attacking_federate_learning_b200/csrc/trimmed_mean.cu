@@ -220,7 +220,7 @@ __device__ __forceinline__ float tie_sum(const float (&v)[S], float T, int need,
   return part;
 }
 
-constexpr int kCap = 8;                       // lane-local candidate list capacity (fast path)
+constexpr int kCap = 4;                       // lane-local candidate list capacity (fast path)
 
 // Fast path.  One fused pass over the registers with a model bracket [a, b): counts #{key < a} (and the
 // lane-local dev sum below a), and appends in-bracket elements to a lane-local list in shared memory
@@ -349,7 +349,7 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
 }
 
 template <int S, bool BF16>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 trimmed_mean_kernel(const Params P) {
   extern __shared__ __align__(1024) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots] + scratch
   constexpr int kGroups = S / 4;
@@ -423,7 +423,7 @@ trimmed_mean_kernel(const Params P) {
 #pragma unroll 1
   for (int cw = warp; cw < kWordCols; cw += kWarps) {
     const int jx = (cw >> 2) & 3;
-    uint32_t* scratch = tile + kWordCols * kGroups * 128 + warp * 512;   // 2 KB of per-warp scratch (1 KB aligned)
+    uint32_t* scratch = tile + kWordCols * kGroups * 128 + warp * 256;   // 1 KB of per-warp scratch: lists [kCap][32] + dense [32]
     const uint4* t4 = reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane;
 #pragma unroll 1
     for (int half = 0; half < (BF16 ? 2 : 1); ++half) {
@@ -512,7 +512,7 @@ static double norm_ppf(double pr) {   // Acklam's rational approximation, |error
 
 template <int S>
 static int launch(const Params& P, int dtype, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(S) * 2048 + kWarps * 2048;
+  const size_t smem = static_cast<size_t>(S) * 2048 + kWarps * 1024;
   const int cols = dtype == AFL_BF16 ? 32 : 16;
   const unsigned grid = static_cast<unsigned>(ceil_div64(P.d, cols));
   ProfScope ps("trimmed_mean", stream);
