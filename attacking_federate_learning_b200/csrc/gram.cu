@@ -34,7 +34,7 @@ constexpr int kTmemCols = 512;
 #ifndef AFL_SPLIT_RN
 #define AFL_SPLIT_RN 0
 #endif
-constexpr int kChunk = 4;                    // k-blocks per contiguous K chunk (4 x 128 B = 512 B per row)
+constexpr int kChunkMaxUnused = 4;                    // k-blocks per contiguous K chunk (4 x 128 B = 512 B per row)
 constexpr int kPartElems = 2 * kTileRows * kTileRows;  // per (pair, split): [2][128][128] fp32
 
 struct Params {
@@ -49,6 +49,7 @@ struct Params {
   int rewrite_hi;
   float* parts;       // [pairs][splits][2][128][128]
   int box_rows;       // rows per TMA box (<= 128; rows past it are never written and only feed ignored outputs)
+  int kchunk_log2;    // k-blocks per contiguous K chunk owned by one split (1 << kchunk_log2)
   int loader;         // 0: TMA boxes, 1: cp.async (LDGSTS) rows written in the same swizzled layout
   const float* G;     // matrix base and pitch (elements) for the cp.async loader
   int64_t ld, d;
@@ -93,7 +94,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   // chunks s, s+splits, s+2*splits, ...  At any moment the CTAs of one tile pair therefore read a
   // contiguous band of every row (DRAM pages are consumed whole) instead of 128-byte pieces that are
   // megabytes apart.
-  const int nchunks_total = (p.kblocks + kChunk - 1) / kChunk;
+  const int kChunk = 1 << p.kchunk_log2;
+  const int nchunks_total = (p.kblocks + kChunk - 1) >> p.kchunk_log2;
   const int my_chunks = split < nchunks_total ? (nchunks_total - split + p.splits - 1) / p.splits : 0;
   int nkb = my_chunks * kChunk;
   if (my_chunks > 0 && split + (my_chunks - 1) * p.splits == nchunks_total - 1)
@@ -140,7 +142,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       for (int it = j; it < nkb; it += 2) {
         mbar_wait_warp(&empty_bar[s], ph ^ 1);
         if (lane == 0) trace_ev(p, it, 1);
-        const int col = ((split + (it / kChunk) * p.splits) * kChunk + (it % kChunk)) * kBK + c16 * 4;
+        const int col = ((split + (it >> p.kchunk_log2) * p.splits) * kChunk + (it & (kChunk - 1))) * kBK + c16 * 4;
         const int64_t remain = p.d - col;
         const uint32_t nbytes = remain >= 4 ? 16u : (remain > 0 ? static_cast<uint32_t>(remain) * 4u : 0u);
         const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
@@ -461,7 +463,7 @@ static EncodeTiledFn encode_fn() {
 
 struct Plan {
   bool tensor;
-  int tiles, splits, stages, stage_bytes, flush;
+  int tiles, splits, stages, stage_bytes, flush, kchunk_log2;
   int simt_splits;
   size_t parts_bytes, s_bytes, total;
 };
@@ -483,6 +485,10 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
   if (pl.tensor) {
     pl.tiles = (n + kTileRows - 1) / kTileRows;
     const int pairs = pl.tiles * pl.tiles;
+    int kc_log2 = env_int("AFL_GRAM_KCHUNK_LOG2", 0);
+    if (kc_log2 < 0 || kc_log2 > 4) kc_log2 = 0;
+    pl.kchunk_log2 = kc_log2;
+    const int kChunk = 1 << kc_log2;
     const int kblocks = (static_cast<int>((d + kBK - 1) / kBK) + kChunk - 1) / kChunk;   // in chunks
     // choose K-splits so that pairs*splits fills an integer number of waves as well as possible
     int best = 1; double best_eff = -1.0;
@@ -558,6 +564,7 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     p.flush = pl.flush; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
     p.single_pass = (flags & AFL_GRAM_SINGLE_PASS) ? 1 : 0;
     p.box_rows = box_rows;
+    p.kchunk_log2 = pl.kchunk_log2;
     p.loader = env_int("AFL_GRAM_LOADER", 0) ? 1 : 0;
     p.G = static_cast<const float*>(G); p.ld = ld; p.d = d;
     p.rewrite_hi = 0;   // AFL_GRAM_REWRITE_HI is accepted but ignored: kind::tf32 was measured to truncate

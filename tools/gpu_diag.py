@@ -258,6 +258,9 @@ reg("c2_box104", case_gram, 100, 11_200_000, F["TC"], "c2_box104", True, env={"A
 reg("c2_box104_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], "c2_box104_single", True, env={"AFL_GRAM_BOXROWS": "104"})
 reg("ident_cpasync", case_gram_identical, 40, 5000, F["TC"], env={"AFL_GRAM_LOADER": "1"})
 reg("n200_cpasync", case_gram, 200, 4096, F["TC"], "tc", env={"AFL_GRAM_LOADER": "1"})
+for kc in ["0","1","2","3"]:
+    reg(f"c2_kc{kc}", case_gram, 100, 11_200_000, F["TC"], f"c2_kc{kc}", True, env={"AFL_GRAM_KCHUNK_LOG2": kc})
+    reg(f"c2_kc{kc}_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], f"c2_kc{kc}_single", True, env={"AFL_GRAM_KCHUNK_LOG2": kc})
 reg("n500_gram", case_gram, 500, 1 << 20, F["TC"], "n500", True)
 reg("n1000_gram", case_gram, 1000, 1 << 19, F["TC"], "n1000", True)
 reg("select_10", case_select, 10, 2, 0)
