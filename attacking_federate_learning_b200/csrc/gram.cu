@@ -34,7 +34,7 @@ constexpr int kTmemCols = 512;
 #ifndef AFL_SPLIT_RN
 #define AFL_SPLIT_RN 0
 #endif
-constexpr int kChunkMaxUnused = 4;                    // k-blocks per contiguous K chunk (4 x 128 B = 512 B per row)
+
 constexpr int kPartElems = 2 * kTileRows * kTileRows;  // per (pair, split): [2][128][128] fp32
 
 struct Params {
