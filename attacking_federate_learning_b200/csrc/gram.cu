@@ -76,7 +76,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   // contract, so align by hand (the host adds 1 KB of slack).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2], first_issued[2];
+  __shared__ __align__(8) uint64_t full_bar[16], empty_bar[16], acc_full[2], acc_empty[2], first_issued[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -503,8 +503,23 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     pl.splits = env_int("AFL_GRAM_SPLITS", best);
     if (pl.splits > kblocks) pl.splits = kblocks;
     if (pl.splits < 1) pl.splits = 1;
-    pl.stage_bytes = (pl.tiles == 1) ? 2 * kTileBytes : 3 * kTileBytes;
-    pl.stages = (pl.tiles == 1) ? 6 : 4;
+    if (pl.tiles == 1) {
+      // single tile: a stage is exactly raw(nb rows) || lo(nb rows); the ring is as deep as shared memory allows
+      const int nb = (n + 15) & ~15;
+      pl.stage_bytes = 2 * nb * 128;
+      // the A operand always spans 128 rows from the stage base: keep that inside the allocation
+      const int slack = (2 * nb < kTileRows) ? (kTileRows - 2 * nb) * 128 : 0;
+      int st = (225 * 1024 - slack) / pl.stage_bytes;
+      if (st > 14) st = 14;                            // named barrier ids 1..15
+      st &= ~1;                                        // even: the two MMA issuers alternate stages
+      pl.stages = env_int("AFL_GRAM_STAGES", st);
+      if (pl.stages > st) pl.stages = st;
+      if (pl.stages < 2) pl.stages = 2;
+      pl.stages &= ~1;
+    } else {
+      pl.stage_bytes = 3 * kTileBytes;
+      pl.stages = 4;
+    }
     pl.flush = env_int("AFL_GRAM_FLUSH", 4);
     if (pl.flush < 2) pl.flush = 2;
     pl.flush &= ~1;                                     // even: the two issuers alternate k-blocks
@@ -551,7 +566,8 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
-    int box_rows = env_int("AFL_GRAM_BOXROWS", kTileRows);
+    int box_rows = kTileRows;
+    if (pl.tiles == 1) box_rows = (n + 15) & ~15;     // rows n..nb-1 are TMA zero fill; nothing past nb is written
     if (box_rows < 8 || box_rows > kTileRows || pl.tiles > 1) box_rows = kTileRows;
     const cuuint32_t box[2] = {kBK, static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t estride[2] = {1, 1};
@@ -570,10 +586,11 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     p.rewrite_hi = 0;   // AFL_GRAM_REWRITE_HI is accepted but ignored: kind::tf32 was measured to truncate
     p.parts = static_cast<float*>(ws);
     double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
-    const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024;
+    const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 +
+                        ((pl.tiles == 1 && pl.stage_bytes < kTileBytes) ? (kTileBytes - pl.stage_bytes) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-      AFL_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      AFL_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr_set = true;
     }
     const char* trace_path = getenv("AFL_GRAM_TRACE");      // debug aid: dump per-role clock64 timestamps

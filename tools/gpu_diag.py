@@ -264,6 +264,9 @@ for kc in ["0","1","2","3"]:
 for sp in ["37","74","148"]:
     reg(f"c2_sp{sp}_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], f"c2_sp{sp}_single", True, env={"AFL_GRAM_SPLITS": sp})
     reg(f"c2_sp{sp}", case_gram, 100, 11_200_000, F["TC"], f"c2_sp{sp}", True, env={"AFL_GRAM_SPLITS": sp})
+for stg in ["4","6","8"]:
+    reg(f"c2_st{stg}", case_gram, 100, 11_200_000, F["TC"], f"c2_st{stg}", True, env={"AFL_GRAM_STAGES": stg})
+    reg(f"c2_st{stg}_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], f"c2_st{stg}_single", True, env={"AFL_GRAM_STAGES": stg})
 reg("n500_gram", case_gram, 500, 1 << 20, F["TC"], "n500", True)
 reg("n1000_gram", case_gram, 1000, 1 << 19, F["TC"], "n1000", True)
 reg("select_10", case_select, 10, 2, 0)
