@@ -41,14 +41,14 @@ class Workspace:
         return buf
 
 
-def sqdist_partial(G: torch.Tensor, flags: int = 0) -> torch.Tensor:
+def sqdist_partial(G: torch.Tensor, flags: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
     """Partial squared-distance table (float64 [n, n]) of this column shard."""
     n, d, ld = check_matrix(G)
     L = nat.lib()
     with torch.cuda.device(G.device):
         nbytes = L.afl_sqdist_workspace_bytes(n, d, dtype_code(G), flags)
         ws = Workspace.get(G.device, "gram", nbytes)
-        d2 = torch.empty((n, n), dtype=torch.float64, device=G.device)
+        d2 = out if out is not None else torch.empty((n, n), dtype=torch.float64, device=G.device)
         nat.check(L.afl_sqdist_partial(G.data_ptr(), n, d, ld, dtype_code(G), d2.data_ptr(), ws.data_ptr(), ws.numel(),
                                        flags, _stream_ptr(G)))
     return d2
@@ -73,6 +73,20 @@ def krum_select(dist: torch.Tensor, users_count: int, corrupted_count: int, want
                                     scores.data_ptr() if want_scores else None, ws.data_ptr(), ws.numel(),
                                     _stream_ptr(dist)))
     return (idx, scores) if want_scores else idx
+
+
+def krum_from_sqdist(d2: torch.Tensor, users_count: int, corrupted_count: int, idx: torch.Tensor | None = None):
+    """(all-reduced) squared-distance table -> device int32[1] Krum index, one FFI call."""
+    n = d2.shape[0]
+    L = nat.lib()
+    with torch.cuda.device(d2.device):
+        ws = Workspace.get(d2.device, "select", L.afl_select_workspace_bytes(n))
+        scratch = Workspace.get(d2.device, "dist", n * n * 4)
+        if idx is None:
+            idx = torch.empty(1, dtype=torch.int32, device=d2.device)
+        nat.check(L.afl_krum_from_sqdist(d2.data_ptr(), n, users_count, corrupted_count, scratch.data_ptr(),
+                                         idx.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(d2)))
+    return idx
 
 
 def bulyan_select(dist: torch.Tensor, users_count: int, corrupted_count: int) -> torch.Tensor:

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libafl_b200.so")
 AFL_OK, AFL_ERR_BAD_ARG, AFL_ERR_PRECONDITION, AFL_ERR_CUDA, AFL_ERR_UNSUPPORTED, AFL_ERR_WORKSPACE = range(6)
 AFL_F32, AFL_BF16 = 0, 1
 GRAM_AUTO, GRAM_FORCE_SIMT, GRAM_FORCE_TCGEN05, GRAM_SINGLE_PASS, GRAM_REWRITE_HI = 0, 1, 2, 4, 8
+GRAM_TF32X2 = 16
 
 _vp, _i, _i64, _sz, _d, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double, C.c_float
 
@@ -30,6 +31,7 @@ SIGNATURES = {
     "afl_sqdist_to_dist": (_i, [_vp, _i, _vp, _vp]),
     "afl_select_workspace_bytes": (_sz, [_i]),
     "afl_krum_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "afl_krum_from_sqdist": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "afl_bulyan_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "afl_trimmed_mean": (_i, [_vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp]),
     "afl_gather_row": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),

@@ -294,6 +294,13 @@ int afl_krum_select(const float* dist, int n, int users_count, int corrupted_cou
   return select::krum_select(dist, n, users_count, corrupted_count, idx_out, scores_out, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
 }
+int afl_krum_from_sqdist(const double* d2, int n, int users_count, int corrupted_count, float* dist_scratch,
+                         int* idx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = gram::sqdist_to_dist(d2, n, dist_scratch, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  return select::krum_select(dist_scratch, n, users_count, corrupted_count, idx_out, nullptr, workspace,
+                             workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 int afl_bulyan_select(const float* dist, int n, int users_count, int corrupted_count, int* sel_out, void* workspace,
                       size_t workspace_bytes, void* stream) {
   return select::bulyan_select(dist, n, users_count, corrupted_count, sel_out, workspace, workspace_bytes,

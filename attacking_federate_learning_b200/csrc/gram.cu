@@ -329,37 +329,51 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   }
 }
 
-// S_ij = sum over splits (fixed order, float64) of  hh_ij + x_ij + x_ji ;  then d2 = s_ii + s_jj - 2 s_ij.
-__global__ void gram_reduce_kernel(const float* __restrict__ parts, int n, int tiles, int splits,
-                                   double* __restrict__ S) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
-  if (j >= n) return;
-  const int ti = i >> 7, ii = i & 127, tj = j >> 7, jj = j & 127;
-  const size_t tile = static_cast<size_t>(kTileRows) * kTileRows;
-  const float* pij = parts + static_cast<size_t>(ti * tiles + tj) * splits * kPartElems;
-  const float* pji = parts + static_cast<size_t>(tj * tiles + ti) * splits * kPartElems;
+// Split reduction.  parts[pair][split][a][128][128] -> HX[a][n][n] (float64), a = 0: sum of hi*hi^T,
+// a = 1: sum of hi*lo^T.  One block per (row i, accumulator a); threadIdx.x walks the columns (coalesced),
+// threadIdx.y owns a fixed, contiguous range of splits; the kSy partial sums are then added in a fixed
+// order, so the result is bit-reproducible and rows that were identical on input stay identical.
+constexpr int kSy = 8;
+__global__ void __launch_bounds__(128 * kSy)
+gram_reduce_kernel(const float* __restrict__ parts, int n, int tiles, int splits, double* __restrict__ HX) {
+  __shared__ double sh[kSy][128];
+  const int i = blockIdx.x, a = blockIdx.y, tj = blockIdx.z;
+  const int jj = threadIdx.x, sy = threadIdx.y;
+  const int j = tj * kTileRows + jj;
+  const int ti = i >> 7, ii = i & 127;
+  const float* base = parts + static_cast<size_t>(ti * tiles + tj) * splits * kPartElems +
+                      static_cast<size_t>(a) * kTileRows * kTileRows + ii * kTileRows + jj;
+  const int s0 = splits * sy / kSy, s1 = splits * (sy + 1) / kSy;
   double acc = 0.0;
-  for (int s = 0; s < splits; ++s) {
-    const float* a = pij + static_cast<size_t>(s) * kPartElems;
-    const float* b = pji + static_cast<size_t>(s) * kPartElems;
-    const double hh = a[ii * kTileRows + jj];
-    const double x1 = a[tile + ii * kTileRows + jj];
-    const double x2 = b[tile + jj * kTileRows + ii];
-    acc += hh + (x1 + x2);   // x1 + x2 is commutative -> S_ij and S_ji get identical bits
+  if (j < n)
+    for (int s = s0; s < s1; ++s) acc += static_cast<double>(base[static_cast<size_t>(s) * kPartElems]);
+  sh[sy][jj] = acc;
+  __syncthreads();
+  if (sy == 0 && j < n) {
+    double t = sh[0][jj];
+#pragma unroll
+    for (int y = 1; y < kSy; ++y) t += sh[y][jj];
+    HX[(static_cast<size_t>(a) * n + i) * n + j] = t;
   }
-  S[static_cast<size_t>(i) * n + j] = acc;
 }
 
-__global__ void gram_to_sqdist_kernel(const double* __restrict__ S, int n, double* __restrict__ d2) {
+// d2_ij = s_ii + s_jj - 2 s_ij with s_ij = hh_ij + (x_ij + x_ji); x_ij + x_ji is commutative, so s (and d2)
+// are exactly symmetric, and identical rows give exact zeros.
+__global__ void gram_to_sqdist_kernel(const double* __restrict__ HX, int n, double* __restrict__ d2) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (j >= n) return;
+  const double* H = HX;
+  const double* X = HX + static_cast<size_t>(n) * n;
   double v = 0.0;
   if (i != j) {
-    const int lo = min(i, j), hi = max(i, j);           // read one triangle so d2 is exactly symmetric
-    v = (S[static_cast<size_t>(lo) * n + lo] + S[static_cast<size_t>(hi) * n + hi]) -
-        2.0 * S[static_cast<size_t>(lo) * n + hi];
+    const int lo = min(i, j), hi = max(i, j);
+    const size_t ll = static_cast<size_t>(lo) * n + lo, hh = static_cast<size_t>(hi) * n + hi;
+    const size_t lh = static_cast<size_t>(lo) * n + hi, hl = static_cast<size_t>(hi) * n + lo;
+    const double s_ll = H[ll] + (X[ll] + X[ll]);
+    const double s_hh = H[hh] + (X[hh] + X[hh]);
+    const double s_lh = H[lh] + (X[lh] + X[hl]);
+    v = (s_ll + s_hh) - 2.0 * s_lh;
   }
   d2[static_cast<size_t>(i) * n + j] = v;
 }
@@ -442,6 +456,11 @@ __global__ void sqdist_to_dist_kernel(const double* __restrict__ d2, int n, floa
   dist[e] = (i == j) ? 0.f : static_cast<float>(sqrt(v > 0.0 ? v : 0.0));
 }
 
+// streaming bf16x2 kernel (gram_bf16.cu)
+bool bf16x2_eligible(int n, int64_t d);
+int bf16x2_splits(int64_t d);
+int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, int splits, int flush, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -463,6 +482,7 @@ static EncodeTiledFn encode_fn() {
 
 struct Plan {
   bool tensor;
+  bool bf16;          // streaming bf16x2 kernel (gram_bf16.cu) instead of the TMA + split-TF32 kernel
   int tiles, splits, stages, stage_bytes, flush, kchunk_log2;
   int simt_splits;
   size_t parts_bytes, s_bytes, total;
@@ -484,6 +504,9 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
   const int sms = sm_count();
   if (pl.tensor) {
     pl.tiles = (n + kTileRows - 1) / kTileRows;
+    const char* kenv = getenv("AFL_GRAM_KERNEL");
+    pl.bf16 = bf16x2_eligible(n, d) && !(flags & (AFL_GRAM_SINGLE_PASS | AFL_GRAM_TF32X2)) &&
+              !(kenv && kenv[0] == 't');
     const int pairs = pl.tiles * pl.tiles;
     int kc_log2 = env_int("AFL_GRAM_KCHUNK_LOG2", 0);
     if (kc_log2 < 0 || kc_log2 > 4) kc_log2 = 0;
@@ -523,8 +546,9 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     pl.flush = env_int("AFL_GRAM_FLUSH", 4);
     if (pl.flush < 2) pl.flush = 2;
     pl.flush &= ~1;                                     // even: the two issuers alternate k-blocks
+    if (pl.bf16) pl.splits = bf16x2_splits(d);
     pl.parts_bytes = static_cast<size_t>(pairs) * pl.splits * kPartElems * sizeof(float);
-    pl.s_bytes = align_up(static_cast<size_t>(n) * n * sizeof(double), 256);
+    pl.s_bytes = align_up(2 * static_cast<size_t>(n) * n * sizeof(double), 256);
     pl.total = pl.parts_bytes + pl.s_bytes;
   } else {
     const int t32 = (n + 31) / 32;
@@ -561,6 +585,17 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
   }
   const dim3 rblock(128), rgrid((n + 127) / 128, n);
   if (pl.tensor) {
+    if (pl.bf16) {
+      float* parts = static_cast<float*>(ws);
+      double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
+      int rc = launch_bf16x2(static_cast<const float*>(G), n, d, ld, parts, pl.splits, pl.flush, stream);
+      if (rc) return rc;
+      gram_reduce_kernel<<<dim3(n, 2, 1), dim3(128, kSy), 0, stream>>>(parts, n, 1, pl.splits, S);
+      AFL_LAUNCH_CHECK("gram_reduce_kernel");
+      gram_to_sqdist_kernel<<<rgrid, rblock, 0, stream>>>(S, n, d2_out);
+      AFL_LAUNCH_CHECK("gram_to_sqdist_kernel");
+      return AFL_OK;
+    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return AFL_ERR_CUDA; }
     CUtensorMap tmap;
@@ -618,7 +653,7 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
       }
     }
     AFL_LAUNCH_CHECK("gram_tcgen05_kernel");
-    gram_reduce_kernel<<<rgrid, rblock, 0, stream>>>(p.parts, n, pl.tiles, pl.splits, S);
+    gram_reduce_kernel<<<dim3(n, 2, pl.tiles), dim3(128, kSy), 0, stream>>>(p.parts, n, pl.tiles, pl.splits, S);
     AFL_LAUNCH_CHECK("gram_reduce_kernel");
     gram_to_sqdist_kernel<<<rgrid, rblock, 0, stream>>>(S, n, d2_out);
     AFL_LAUNCH_CHECK("gram_to_sqdist_kernel");

@@ -33,6 +33,7 @@ class ShardedAggregator:
         self.k = kernels if kernels is not None else NativeKernels()
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._buf = {}
 
     # -- the single exchange step of the path
     def _allreduce_table(self, d2):
@@ -43,10 +44,24 @@ class ShardedAggregator:
     def distances(self, G_shard):
         return self.k.sqdist_to_dist(self._allreduce_table(self.k.sqdist_partial(G_shard)))
 
+    def _buffers(self, n, device):
+        key = (n, str(device))
+        if self._buf.get("key") != key:
+            self._buf = {"key": key, "d2": torch.empty((n, n), dtype=torch.float64, device=device),
+                         "idx": torch.empty(1, dtype=torch.int32, device=device)}
+        return self._buf["d2"], self._buf["idx"]
+
     def krum(self, G_shard, users_count, corrupted_count, return_index=False):
         if not return_index:
             assert users_count >= 2 * corrupted_count + 1, ('users_count>=2*corrupted_count + 3', users_count, corrupted_count)
-        idx = int(self.k.krum_select(self.distances(G_shard), users_count, corrupted_count).reshape(-1)[0].item())
+        if hasattr(self.k, "krum_from_sqdist"):
+            # hot path: two FFI crossings + the one all-reduce, persistent buffers, one 4-byte D2H sync
+            d2, idx_dev = self._buffers(G_shard.shape[0], G_shard.device)
+            self.k.sqdist_partial(G_shard, 0, d2)
+            self._allreduce_table(d2)
+            idx = int(self.k.krum_from_sqdist(d2, users_count, corrupted_count, idx_dev).item())
+        else:
+            idx = int(self.k.krum_select(self.distances(G_shard), users_count, corrupted_count).reshape(-1)[0].item())
         return idx if return_index else G_shard[idx]
 
     def bulyan(self, G_shard, users_count, corrupted_count, return_selection=False):

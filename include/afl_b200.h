@@ -53,6 +53,7 @@ enum {
   AFL_GRAM_FORCE_SIMT = 1,    /* CUDA-core difference kernel (verification / unaligned pitch)      */
   AFL_GRAM_FORCE_TCGEN05 = 2, /* fail with AFL_ERR_UNSUPPORTED instead of falling back to SIMT     */
   AFL_GRAM_SINGLE_PASS = 4,   /* tcgen05: hi*hi only (plain TF32), for measurement                  */
+  AFL_GRAM_TF32X2 = 16,       /* tcgen05: always the TMA + split-TF32 kernel (skip the streaming bf16x2 kernel) */
   AFL_GRAM_REWRITE_HI = 8     /* accepted, ignored (kind::tf32 was measured to ignore the low 13     */
                               /* mantissa bits of fp32 operands, which is what the split relies on)  */
 };
@@ -97,6 +98,11 @@ int afl_sqdist_to_dist(const double* d2, int n, float* dist, void* stream);
 size_t afl_select_workspace_bytes(int n);
 int afl_krum_select(const float* dist, int n, int users_count, int corrupted_count, int* idx_out,
                     float* scores_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Convenience: afl_sqdist_to_dist + afl_krum_select in one call (one FFI crossing per aggregation after
+ * the all-reduce).  dist_scratch: device float[n*n]. */
+int afl_krum_from_sqdist(const double* d2, int n, int users_count, int corrupted_count, float* dist_scratch,
+                         int* idx_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Bulyan selection:  defences.py:57-68 ------------------------------------------------------
  * theta = users_count - 2f rounds of Krum-with-removal on one distance table; sel_out (device
