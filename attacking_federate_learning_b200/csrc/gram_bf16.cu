@@ -41,6 +41,7 @@ struct B16Params {
   int kblocks;          // ceil(d / 64)
   int flush;            // k-blocks per TMEM accumulation chain (even)
   float* parts;         // [splits][2][128][128]
+  int prefetch;         // L2 prefetch distance in this warp's own k-blocks (0 = off)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
@@ -63,6 +64,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 // c_format F32 (1) [4,6) | a_format BF16 (1) [7,10) | b_format BF16 (1) [10,13) | K-major | n>>3 | m>>4
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Pull one k-block's worth of this warp's rows (256 contiguous bytes each) into L2, without registers.
+__device__ __forceinline__ void prefetch_rows_l2(const B16Params& p, int64_t col0, int lane) {
+  if (col0 >= p.d) return;
+  const int64_t remain = p.d - col0;
+  const uint32_t bytes = remain >= kB16Cols ? 256u : static_cast<uint32_t>(remain / 4) * 16u;
+  if (bytes == 0) return;
+  for (int r = lane; r < p.n; r += 32) {
+    const float* src = p.G + static_cast<int64_t>(r) * p.ld + col0;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+  }
 }
 
 constexpr int kPassPerBatch = 4;     // 4 passes x 2 x LDG.128 = 8 loads (32 registers) per batch, double-buffered
@@ -204,8 +217,13 @@ gram_bf16x2_kernel(const B16Params p) {
     auto col_of = [&](int kbi) -> int64_t {
       return (static_cast<int64_t>(split) + static_cast<int64_t>(w + kbi * kB16Stages) * p.splits) * kB16Cols + c32 * 8;
     };
+    auto prefetch_for = [&](int kbi) {                    // k-block kbi + distance of THIS warp
+      if (p.prefetch > 0 && kbi + p.prefetch < my_kb) prefetch_rows_l2(p, col_of(kbi + p.prefetch) - c32 * 8, lane);
+    };
     Batch B0, B1;
     if (total > 0) {
+      for (int k = 0; k < p.prefetch && k < my_kb; ++k) prefetch_rows_l2(p, col_of(k) - c32 * 8, lane);
+      prefetch_for(0);
       const int64_t col = col_of(0);
       load_batch(B0, p, p.G + (col < p.d ? col : 0), col, 0, sub);
       if (++b_l == nbatch) { b_l = 0; ++kb_l; }
@@ -213,6 +231,7 @@ gram_bf16x2_kernel(const B16Params p) {
     for (int g = 0; g < total; g += 2) {
       // ---- even position: prefetch into B1, consume B0
       if (g + 1 < total) {
+        if (b_l == 0) prefetch_for(kb_l);
         const int64_t col = col_of(kb_l);
         load_batch(B1, p, p.G + (col < p.d ? col : 0), col, b_l, sub);
         if (++b_l == nbatch) { b_l = 0; ++kb_l; }
@@ -227,6 +246,7 @@ gram_bf16x2_kernel(const B16Params p) {
       if (g + 1 >= total) break;
       // ---- odd position: prefetch into B0, consume B1
       if (g + 2 < total) {
+        if (b_l == 0) prefetch_for(kb_l);
         const int64_t col = col_of(kb_l);
         load_batch(B0, p, p.G + (col < p.d ? col : 0), col, b_l, sub);
         if (++b_l == nbatch) { b_l = 0; ++kb_l; }
@@ -308,6 +328,8 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
   p.kblocks = static_cast<int>((d + kB16Cols - 1) / kB16Cols);
   p.flush = flush < 2 ? 2 : (flush & ~1);
   p.parts = parts;
+  p.prefetch = 1;
+  if (const char* e = getenv("AFL_GRAM_PREFETCH")) p.prefetch = atoi(e) < 0 ? 0 : atoi(e);
   const size_t smem = static_cast<size_t>(kB16Stages) * p.nb * 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {

@@ -277,6 +277,8 @@ reg("b16_ident", case_gram_identical, 100, 70_000, F["TC"])
 for sp in ["37","74"]:
     reg(f"b16_sp{sp}", case_gram, 100, 11_200_000, F["TC"], f"b16_sp{sp}", True, env={"AFL_GRAM_SPLITS": sp})
 reg("b16_flush2", case_gram, 100, 11_200_000, F["TC"], "b16_flush2", True, env={"AFL_GRAM_FLUSH": "2"})
+for pf in ["0","1","2","4"]:
+    reg(f"b16_pf{pf}", case_gram, 100, 11_200_000, F["TC"], f"b16_pf{pf}", True, env={"AFL_GRAM_PREFETCH": pf})
 reg("n500_gram", case_gram, 500, 1 << 20, F["TC"], "n500", True)
 reg("n1000_gram", case_gram, 1000, 1 << 19, F["TC"], "n1000", True)
 reg("select_10", case_select, 10, 2, 0)
