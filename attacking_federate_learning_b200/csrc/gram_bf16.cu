@@ -42,6 +42,7 @@ struct B16Params {
   int flush;            // k-blocks per TMEM accumulation chain (even)
   float* parts;         // [splits][2][128][128]
   int prefetch;         // L2 prefetch distance in this warp's own k-blocks (0 = off)
+  int knock;            // debug knock-outs: 1 no MMA, 2 no smem stores, 4 no global loads
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void load_batch(Batch& B, const B16Params& p, const f
   for (int q = 0; q < kPassPerBatch; ++q) {
     const int row = 4 * (kPassPerBatch * b + q) + sub;
     float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-    if (row < p.n) {
+    if (row < p.n && !(p.knock & 4)) {
       const float* src = gcol + static_cast<int64_t>(row) * p.ld;
       if (full) {
         x0 = ldg_stream_f4(reinterpret_cast<const float4*>(src));
@@ -112,7 +113,7 @@ __device__ __forceinline__ void store_batch(const Batch& B, const B16Params& p, 
 #pragma unroll
   for (int q = 0; q < kPassPerBatch; ++q) {
     const int row = 4 * (kPassPerBatch * b + q) + sub;
-    if (row < p.n) {
+    if (row < p.n && !(p.knock & 2)) {
       const float x[8] = {B.v[q][0].x, B.v[q][0].y, B.v[q][0].z, B.v[q][0].w,
                           B.v[q][1].x, B.v[q][1].y, B.v[q][1].z, B.v[q][1].w};
       uint32_t h[4], l[4];
@@ -186,6 +187,7 @@ gram_bf16x2_kernel(const B16Params p) {
           const uint32_t st = smem_base + static_cast<uint32_t>(s) * stage_bytes;
           const uint64_t dab = umma_desc_sw128(st);      // A = rows 0..127 of the stage, B = rows 0..2nb-1
           if (elect_one()) {
+            if (!(p.knock & 1))
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)               // 4 x K=16 bf16 = 64 columns; +32 bytes per step
               umma_bf16(d_acc, dab + static_cast<uint64_t>(ks * 2), dab + static_cast<uint64_t>(ks * 2), idesc,
@@ -328,7 +330,8 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
   p.kblocks = static_cast<int>((d + kB16Cols - 1) / kB16Cols);
   p.flush = flush < 2 ? 2 : (flush & ~1);
   p.parts = parts;
-  p.prefetch = 1;
+  p.prefetch = 0;
+  if (const char* e = getenv("AFL_GRAM_KNOCK")) p.knock = atoi(e);
   if (const char* e = getenv("AFL_GRAM_PREFETCH")) p.prefetch = atoi(e) < 0 ? 0 : atoi(e);
   const size_t smem = static_cast<size_t>(kB16Stages) * p.nb * 256 + 1024;
   static bool attr_set = false;
