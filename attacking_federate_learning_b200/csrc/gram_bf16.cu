@@ -79,7 +79,8 @@ __device__ __forceinline__ void prefetch_rows_l2(const B16Params& p, int64_t col
   }
 }
 
-constexpr int kPassPerBatch = 4;     // 4 passes x 2 x LDG.128 = 8 loads (32 registers) per batch, double-buffered
+constexpr int kPassPerBatch = 3;     // 3 passes x 2 x LDG.128 = 6 loads (24 registers) per batch, triple-buffered:
+                                     // two batches (12 loads per lane, ~49 KB per SM) are in flight while one is consumed
 
 struct Batch { float4 v[kPassPerBatch][2]; };
 
@@ -222,43 +223,33 @@ gram_bf16x2_kernel(const B16Params p) {
     auto prefetch_for = [&](int kbi) {                    // k-block kbi + distance of THIS warp
       if (p.prefetch > 0 && kbi + p.prefetch < my_kb) prefetch_rows_l2(p, col_of(kbi + p.prefetch) - c32 * 8, lane);
     };
-    Batch B0, B1;
+    Batch B0, B1, B2;
+    auto issue = [&](Batch& B) {                          // load the next batch of the stream (if any)
+      if (kb_l >= my_kb) return;
+      if (b_l == 0) prefetch_for(kb_l);
+      const int64_t col = col_of(kb_l);
+      load_batch(B, p, p.G + (col < p.d ? col : 0), col, b_l, sub);
+      if (++b_l == nbatch) { b_l = 0; ++kb_l; }
+    };
+    auto consume = [&](const Batch& B) {                  // convert + store the oldest batch in flight
+      if (b_s == 0) mbar_wait_warp(&empty_bar[w], (kb_s & 1) ^ 1);
+      store_batch(B, p, st, b_s, sub, c32);
+      if (++b_s == nbatch) {
+        b_s = 0; ++kb_s;
+        fence_proxy_async_smem();
+        named_bar_arrive(1 + w, 64);
+      }
+    };
     if (total > 0) {
       for (int k = 0; k < p.prefetch && k < my_kb; ++k) prefetch_rows_l2(p, col_of(k) - c32 * 8, lane);
-      prefetch_for(0);
-      const int64_t col = col_of(0);
-      load_batch(B0, p, p.G + (col < p.d ? col : 0), col, 0, sub);
-      if (++b_l == nbatch) { b_l = 0; ++kb_l; }
-    }
-    for (int g = 0; g < total; g += 2) {
-      // ---- even position: prefetch into B1, consume B0
-      if (g + 1 < total) {
-        if (b_l == 0) prefetch_for(kb_l);
-        const int64_t col = col_of(kb_l);
-        load_batch(B1, p, p.G + (col < p.d ? col : 0), col, b_l, sub);
-        if (++b_l == nbatch) { b_l = 0; ++kb_l; }
-      }
-      if (b_s == 0) mbar_wait_warp(&empty_bar[w], (kb_s & 1) ^ 1);
-      store_batch(B0, p, st, b_s, sub, c32);
-      if (++b_s == nbatch) {
-        b_s = 0; ++kb_s;
-        fence_proxy_async_smem();
-        named_bar_arrive(1 + w, 64);
-      }
-      if (g + 1 >= total) break;
-      // ---- odd position: prefetch into B0, consume B1
-      if (g + 2 < total) {
-        if (b_l == 0) prefetch_for(kb_l);
-        const int64_t col = col_of(kb_l);
-        load_batch(B0, p, p.G + (col < p.d ? col : 0), col, b_l, sub);
-        if (++b_l == nbatch) { b_l = 0; ++kb_l; }
-      }
-      if (b_s == 0) mbar_wait_warp(&empty_bar[w], (kb_s & 1) ^ 1);
-      store_batch(B1, p, st, b_s, sub, c32);
-      if (++b_s == nbatch) {
-        b_s = 0; ++kb_s;
-        fence_proxy_async_smem();
-        named_bar_arrive(1 + w, 64);
+      issue(B0);
+      issue(B1);
+      for (int g = 0; g < total; g += 3) {
+        issue(B2); consume(B0);
+        if (g + 1 >= total) break;
+        issue(B0); consume(B1);
+        if (g + 2 >= total) break;
+        issue(B1); consume(B2);
       }
     }
   } else {

@@ -129,14 +129,20 @@ def test_krum_matches_oracle(api, n, d, f, seed):
     assert D.krum(Gd, n, f, return_index=True) == want
     row = D.krum(Gd, n, f)
     assert row.data_ptr() == Gd[want].data_ptr()                              # a view, like the reference
-    # the tensor-core table agrees with the float64 arbiter far inside the oracle's own fp32 noise
+    # Tensor-core tables vs the float64 arbiter.  Both tensor kernels carry a small UNIFORM scale bias
+    # (tensor-core accumulation truncates; the bf16x2 kernel also drops the b2*b2 term) which cannot
+    # change any ranking; what must be tiny is the pair-to-pair SPREAD of the relative error.
     Gp = torch.zeros((n, (d + 3) // 4 * 4), device="cuda")[:, :d]; Gp.copy_(Gd)
-    d2 = dev.sqdist_partial(Gp, nat.GRAM_FORCE_TCGEN05).cpu().numpy()
     off = ~np.eye(n, dtype=bool)
-    rel = np.abs(d2 - table64 ** 2)[off] / (table64 ** 2)[off]
-    assert rel.max() < 2e-6, rel.max()
+    ref2 = (table64 ** 2)[off]
+    for flags, bias_cap in ((nat.GRAM_FORCE_TCGEN05, 6e-6), (nat.GRAM_FORCE_TCGEN05 | nat.GRAM_TF32X2, 2e-6)):
+        d2 = dev.sqdist_partial(Gp, flags).cpu().numpy()
+        rel = (d2[off] - ref2) / ref2
+        assert np.abs(rel).max() < bias_cap, np.abs(rel).max()
+        assert rel.max() - rel.min() < 5e-7, (rel.min(), rel.max())
+        assert np.array_equal(d2, d2.T) and not d2.diagonal().any()
     d2s = dev.sqdist_partial(Gd, nat.GRAM_FORCE_SIMT).cpu().numpy()
-    assert (np.abs(d2s - table64 ** 2)[off] / (table64 ** 2)[off]).max() < 1e-6
+    assert (np.abs(d2s[off] - ref2) / ref2).max() < 1e-6
 
 
 def test_identical_rows_tie_goes_to_user_1(api):
@@ -249,7 +255,7 @@ def test_properties_at_scale(api):
     assert torch.equal(d2, d2.T) and float(torch.diagonal(d2).abs().max()) == 0.0
     ex = torch.cdist(G[:8, :200000].double(), G[:8, :200000].double()) ** 2
     got = dev.sqdist_partial(G[:8, :200000].contiguous())
-    assert float(((got - ex).abs() / ex.clamp_min(1)).max()) < 2e-6
+    assert float(((got - ex).abs() / ex.clamp_min(1)).max()) < 6e-6
     # trimmed mean: constant columns, bounded by the column range, parity with the oracle on a column
     # sample of the big matrix (shift equivariance does NOT hold for this rule: one +T/-T swap at the
     # keep boundary moves the result by 2T/k, so it is not asserted)
