@@ -129,6 +129,8 @@ def test_krum_matches_oracle(api, n, d, f, seed):
     assert D.krum(Gd, n, f, return_index=True) == want
     row = D.krum(Gd, n, f)
     assert row.data_ptr() == Gd[want].data_ptr()                              # a view, like the reference
+    from attacking_federate_learning_b200.sharded import ShardedAggregator
+    assert ShardedAggregator().krum(Gd, n, f, return_index=True) == want      # fused afl_krum_from_sqdist path
     # Tensor-core tables vs the float64 arbiter.  Both tensor kernels carry a small UNIFORM scale bias
     # (tensor-core accumulation truncates; the bf16x2 kernel also drops the b2*b2 term) which cannot
     # change any ranking; what must be tiny is the pair-to-pair SPREAD of the relative error.
