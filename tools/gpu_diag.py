@@ -267,7 +267,7 @@ for sp in ["37","74","148"]:
 for stg in ["4","6","8"]:
     reg(f"c2_st{stg}", case_gram, 100, 11_200_000, F["TC"], f"c2_st{stg}", True, env={"AFL_GRAM_STAGES": stg})
     reg(f"c2_st{stg}_single", case_gram, 100, 11_200_000, F["TC"] | F["SINGLE"], f"c2_st{stg}_single", True, env={"AFL_GRAM_STAGES": stg})
-reg("b16_c2", case_gram, 100, 11_200_000, F["TC"], "b16_c2", True)
+reg("b16_c2", case_gram, 100, 11_200_000, F["TC"] | 32, "b16_c2", True)
 reg("tf32_c2", case_gram, 100, 11_200_000, F["TC"] | 16, "tf32_c2", True)
 reg("b16_ragged", case_gram, 100, 100_004, F["TC"], "b16_ragged")
 reg("b16_n64", case_gram, 64, 65_540, F["TC"], "b16_n64")

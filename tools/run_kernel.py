@@ -11,6 +11,10 @@ if what.startswith("tm"):
         G = G.bfloat16()
     for _ in range(iters):
         dev.trimmed_mean(G, 240)
+elif what == "gram_bf16":
+    G = torch.randn(100, 11_200_000, generator=g, device="cuda")
+    for _ in range(iters):
+        dev.sqdist_partial(G, 32)
 elif what == "gram":
     G = torch.randn(100, 11_200_000, generator=g, device="cuda")
     for _ in range(iters):
