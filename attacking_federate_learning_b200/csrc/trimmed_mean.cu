@@ -288,28 +288,26 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
       const bool have = lane < cin;
       const float val = have ? dense[lane] : kInf;
       const float key = have ? keyof<KEYS>(val) : kInf;
-      int lt = 0, le = 0;                       // candidates with key < mine / <= mine (excluding self in lt only)
+      // rank in the strict order (key, lane): all ranks distinct; 31 shuffles, 3 ALU ops per step
+      int rank = 0;
 #pragma unroll
       for (int t = 1; t < 32; ++t) {
         const float ok = __shfl_sync(0xffffffffu, key, (lane + t) & 31);
-        lt += (ok < key) ? 1 : 0;
-        le += (ok <= key) ? 1 : 0;
+        const bool wrapped = lane >= 32 - t;              // source lane (lane + t) & 31 is below this lane
+        rank += ((ok < key) || (wrapped && ok == key)) ? 1 : 0;
       }
-      le += 1;
       if (!KEYS) {
-        const int t1 = r1 - c_a, t2 = r2 - c_a;
-        const unsigned ma = __ballot_sync(0xffffffffu, have && lt <= t1 && t1 < le);
-        const unsigned mb = __ballot_sync(0xffffffffu, have && lt <= t2 && t2 < le);
+        const unsigned ma = __ballot_sync(0xffffffffu, rank == r1 - c_a);
+        const unsigned mb = __ballot_sync(0xffffffffu, rank == r2 - c_a);
         out_a = __shfl_sync(0xffffffffu, val, __ffs(ma) - 1);
         out_b = __shfl_sync(0xffffffffu, val, __ffs(mb) - 1);
         return true;
       }
       const int take = r1 + 1 - c_a;            // number of candidates kept, in (key, row) order
-      const unsigned mt = __ballot_sync(0xffffffffu, have && lt < take && take <= le);   // the boundary tie group
-      const int src = __ffs(mt) - 1;
-      const float T = __shfl_sync(0xffffffffu, key, src);
-      const int n_less = __shfl_sync(0xffffffffu, lt, src);
-      const int group = __shfl_sync(0xffffffffu, le, src) - n_less;
+      const unsigned mt = __ballot_sync(0xffffffffu, rank == take - 1);          // the boundary candidate
+      const float T = __shfl_sync(0xffffffffu, key, __ffs(mt) - 1);
+      const int n_less = __popc(__ballot_sync(0xffffffffu, have && key < T));
+      const int group = __popc(__ballot_sync(0xffffffffu, have && key == T));
       const int need = take - n_less;
       float part = sa + ((have && key < T) ? val : 0.f);
       if (need == group) part += (have && key == T) ? val : 0.f;     // whole tie group kept: order irrelevant
@@ -442,10 +440,17 @@ trimmed_mean_kernel(const Params P) {
       // mean / sigma of the column (pivot model only; never enters the result)
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < S; ++i) {
-        const bool ok = x[i] < kInf;
-        s1 += ok ? x[i] : 0.f;
-        s2 += ok ? x[i] * x[i] : 0.f;
+      for (int m = 0; m < kGroups; ++m) {
+        if ((4 * m + 4) * 32 <= n) {                    // every row of this slot group exists (warp-uniform)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { s1 += x[4 * m + q]; s2 = fmaf(x[4 * m + q], x[4 * m + q], s2); }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float t = (x[4 * m + q] < kInf) ? x[4 * m + q] : 0.f;   // padded rows are +inf
+            s1 += t; s2 = fmaf(t, t, s2);
+          }
+        }
       }
       s1 = warp_sum(s1); s2 = warp_sum(s2);
       const float mean = s1 / fn;
