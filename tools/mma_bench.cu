@@ -11,13 +11,14 @@ __device__ __forceinline__ void umma_f16k(uint32_t d, uint64_t a, uint64_t b, ui
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1) mma_bench(int n, int bf16, int naccum, int iters, int kadv, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_bench(int n, int bf16, int naccum, int iters, int kadv, long long* out, int commit_every) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t ring[8];
   __shared__ uint32_t tbase;
   for (int i = threadIdx.x; i < (128 + 256) * 128 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&ring[i], 1); fence_mbar_init(); }
   if (threadIdx.x < 32) { tmem_alloc(&tbase, 512); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int n, int bf16, int naccum,
           if (bf16) umma_f16k(d, da + adv, db + adv, idesc, 1);
           else umma_tf32(d, da + adv, db + adv, idesc, 1);
         }
+        if (commit_every && (it % commit_every) == commit_every - 1) umma_commit(&ring[it & 7]);
       }
       umma_commit(&bar);
     }
@@ -59,16 +61,16 @@ int main() {
   long long* out; cudaMalloc(&out, 16);
   cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
   const int iters = 2000;
-  int cfgs[][4] = {{112,0,1,1},{224,0,1,1},{224,0,2,1},{112,1,1,1},{224,1,1,1},{224,1,2,1},{256,1,1,1},{256,0,1,1},{64,0,1,1},{224,0,1,0},{128,0,1,1}};
+  int cfgs[][5] = {{224,0,1,1,0},{224,0,1,1,1},{224,0,1,1,4},{224,1,1,1,1},{112,0,1,1,1},{256,0,1,1,1}};
   for (auto& c : cfgs) {
-    for (int grid : {1, 148}) {
-      mma_bench<<<grid, 128, 52 * 1024>>>(c[0], c[1], c[2], iters, c[3], out);
+    for (int grid : {148}) {
+      mma_bench<<<grid, 128, 52 * 1024>>>(c[0], c[1], c[2], iters, c[3], out, c[4]);
       cudaError_t e = cudaDeviceSynchronize();
       long long h[2]; cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
       const double cyc = double(h[0] - h[1]) / (iters * 4.0);
       const double macs = 128.0 * c[0] * (c[1] ? 16 : 8);
-      printf("N=%3d %s accum=%d kadv=%d grid=%3d : %7.1f cycles/MMA  %7.0f MAC/clk/SM  (%s)\n", c[0], c[1] ? "bf16 K16" : "tf32 K8 ",
-             c[2], c[3], grid, cyc, macs / cyc, cudaGetErrorString(e));
+      printf("N=%3d %s accum=%d commit_every=%d grid=%3d : %7.1f cycles/MMA  %7.0f MAC/clk/SM  (%s)\n", c[0], c[1] ? "bf16 K16" : "tf32 K8 ",
+             c[2], c[4], grid, cyc, macs / cyc, cudaGetErrorString(e));
     }
   }
   return 0;
