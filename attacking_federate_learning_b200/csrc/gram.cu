@@ -46,6 +46,7 @@ struct Params {
   int stages;
   int stage_bytes;    // 32 KB (T == 1: [A][LO]) or 48 KB ([A][B][LO])
   int single_pass;
+  int dbg;            // measurement only: 1 = split work but narrow (hi*hi) MMA, 2 = no split work but wide MMA
   int rewrite_hi;
   float* parts;       // [pairs][splits][2][128][128]
   int box_rows;       // rows per TMA box (<= 128; rows past it are never written and only feed ignored outputs)
@@ -192,7 +193,8 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       // same TMEM buffer; the overwrite (accumulate = 0) MMA of a group is always issuer 0's first,
       // and issuer 1 does not start a group before that MMA has been issued (`first_issued`).
       const int j = (warp == 3) ? 1 : 0;
-      const uint32_t idesc = umma_idesc_tf32(kTileRows, p.single_pass ? nb : 2 * nb);
+      const bool wide = p.dbg == 2 || (!p.single_pass && p.dbg != 1);
+      const uint32_t idesc = umma_idesc_tf32(kTileRows, wide ? 2 * nb : nb);
       int s = j;
       for (int g = 0; g < ngroups; ++g) {
         const int b = g & 1;
@@ -243,7 +245,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       mbar_wait_warp(&full_bar[s], ph);
       if (t == 0) trace_ev(p, it, 2);
       uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
-      if (!p.single_pass) {
+      if (!p.single_pass && p.dbg != 2) {
         const uint32_t src = smem_u32(st + (has_b ? off_b : 0)) + static_cast<uint32_t>(t) * 16u;
         const uint32_t dst = smem_u32(st + off_lo) + static_cast<uint32_t>(t) * 16u;
         float4 v[8];
@@ -617,6 +619,7 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     p.flush = pl.flush; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
     p.single_pass = (flags & AFL_GRAM_SINGLE_PASS) ? 1 : 0;
     p.box_rows = box_rows;
+    p.dbg = env_int("AFL_GRAM_DBG", 0);
     p.kchunk_log2 = pl.kchunk_log2;
     p.loader = env_int("AFL_GRAM_LOADER", 0) ? 1 : 0;
     p.G = static_cast<const float*>(G); p.ld = ld; p.d = d;

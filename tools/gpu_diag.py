@@ -283,6 +283,8 @@ for kn in ["1","2","4","3","6"]:
     reg(f"b16_knock{kn}", case_gram, 100, 11_200_000, F["TC"], f"b16_knock{kn}", True, env={"AFL_GRAM_KNOCK": kn})
 for fl in ["8","32","512"]:
     reg(f"b16_fl{fl}", case_gram, 100, 11_200_000, F["TC"], f"b16_fl{fl}", True, env={"AFL_GRAM_FLUSH": fl})
+for dbg in ["1","2"]:
+    reg(f"c2_dbg{dbg}", case_gram, 100, 11_200_000, F["TC"], f"c2_dbg{dbg}", True, env={"AFL_GRAM_DBG": dbg})
 reg("n500_gram", case_gram, 500, 1 << 20, F["TC"], "n500", True)
 reg("n1000_gram", case_gram, 1000, 1 << 19, F["TC"], "n1000", True)
 reg("select_10", case_select, 10, 2, 0)
