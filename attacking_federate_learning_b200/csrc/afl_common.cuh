@@ -152,6 +152,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Fast-path wait: one probe by every lane (an already-completed phase costs a single try_wait); only if
+// the phase is still pending does lane 0 spin while the others sleep at the warp barrier.
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  mbar_wait_warp(bar, parity);
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

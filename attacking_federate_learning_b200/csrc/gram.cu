@@ -203,13 +203,13 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
         int it = it_begin + j;                          // flush is even: parity of `it` == issuer id
         if (it < it_end) {
-          mbar_wait_warp(&acc_empty[b], gph ^ 1);
-          if (j == 1) mbar_wait_warp(&first_issued[b], gph);
+          mbar_wait_fast(&acc_empty[b], gph ^ 1);
+          if (j == 1) mbar_wait_fast(&first_issued[b], gph);
           tc_fence_after();
         }
         for (; it < it_end; it += 2) {
           if (lane == 0) trace_ev(p, it, 11);
-          named_bar_sync(1 + s, 128 + 32);              // split warps have produced stage s (implies TMA landed)
+          named_bar_sync(1 + s, 32 + 32);               // the split warp owning stage s is done (implies TMA landed)
           if (lane == 0) trace_ev(p, it, 12);
           tc_fence_after();
           const uint32_t st = smem_u32(smem) + static_cast<uint32_t>(s) * static_cast<uint32_t>(p.stage_bytes);
@@ -235,49 +235,52 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
     }
   } else if (wg == 1) {
-    setmaxnreg_dec<64>();
-    // ===================== split warps: lo = RN_tf32(g - hi) =====================
-    const int t = threadIdx.x - 128;
-    const int nchunks_b = nb * 8;           // 16-byte chunks of the B-side tile (rows < nb)
-    int s = 0;
+    setmaxnreg_dec<96>();
+    // ===================== split warps: lo = g - hi, one warp per stage (4 stages in parallel) =====================
+    // hi = what the tensor core keeps of an fp32 operand (top 10 mantissa bits); lo is the exact residual,
+    // stored at the same swizzled byte offsets in the sibling tile (the tensor core truncates it to 11 bits).
+    const int w4 = warp - 4;
+    const int nchunks_b = nb * 8;                         // 16-byte chunks of the B-side tile (rows < nb)
+    int s = w4;
     uint32_t ph = 0;
-    for (int it = 0; it < nkb; ++it) {
-      mbar_wait_warp(&full_bar[s], ph);
-      if (t == 0) trace_ev(p, it, 2);
+    for (int it = w4; it < nkb; it += 4) {
+      mbar_wait_fast(&full_bar[s], ph);
+      if (lane == 0) trace_ev(p, it, 2);
       uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
       if (!p.single_pass && p.dbg != 2) {
-        const uint32_t src = smem_u32(st + (has_b ? off_b : 0)) + static_cast<uint32_t>(t) * 16u;
-        const uint32_t dst = smem_u32(st + off_lo) + static_cast<uint32_t>(t) * 16u;
-        float4 v[8];
+        const uint32_t src = smem_u32(st + (has_b ? off_b : 0)) + static_cast<uint32_t>(lane) * 16u;
+        const uint32_t dst = smem_u32(st + off_lo) + static_cast<uint32_t>(lane) * 16u;
+#pragma unroll 1
+        for (int c0 = 0; c0 < nchunks_b; c0 += 8 * 32) {
+          float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)                       // all loads first: up to 8 LDS.128 in flight per thread
-          if (t + u * 128 < nchunks_b) v[u] = lds128(src + u * 2048);
-        if (t == 0) trace_ev(p, it, 8);
+          for (int u = 0; u < 8; ++u)                     // all loads first: 8 LDS.128 in flight per thread
+            if (c0 + u * 32 + lane < nchunks_b) v[u] = lds128(src + (c0 + u * 32) * 16);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (t + u * 128 < nchunks_b) {
-            float4 l;                                     // hi = what the tensor core keeps of an fp32 operand
+          for (int u = 0; u < 8; ++u) {
+            if (c0 + u * 32 + lane < nchunks_b) {
+              float4 l;
 #if AFL_SPLIT_RN
-            l.x = tf32_rna(v[u].x - tf32_trunc(v[u].x)); l.y = tf32_rna(v[u].y - tf32_trunc(v[u].y));
-            l.z = tf32_rna(v[u].z - tf32_trunc(v[u].z)); l.w = tf32_rna(v[u].w - tf32_trunc(v[u].w));
-#else                                                     // exact residual; the tensor core truncates it to 11 bits
-            l.x = v[u].x - tf32_trunc(v[u].x); l.y = v[u].y - tf32_trunc(v[u].y);
-            l.z = v[u].z - tf32_trunc(v[u].z); l.w = v[u].w - tf32_trunc(v[u].w);
+              l.x = tf32_rna(v[u].x - tf32_trunc(v[u].x)); l.y = tf32_rna(v[u].y - tf32_trunc(v[u].y));
+              l.z = tf32_rna(v[u].z - tf32_trunc(v[u].z)); l.w = tf32_rna(v[u].w - tf32_trunc(v[u].w));
+#else
+              l.x = v[u].x - tf32_trunc(v[u].x); l.y = v[u].y - tf32_trunc(v[u].y);
+              l.z = v[u].z - tf32_trunc(v[u].z); l.w = v[u].w - tf32_trunc(v[u].w);
 #endif
-            sts128(dst + u * 2048, l);
+              sts128(dst + (c0 + u * 32) * 16, l);
+            }
           }
         }
-        if (t == 0) trace_ev(p, it, 9);
         fence_proxy_async_smem();
-        if (t == 0) trace_ev(p, it, 10);
       }
       if (p.single_pass && p.loader == 1) fence_proxy_async_smem();   // cp.async data -> async proxy
-      named_bar_arrive(1 + s, 128 + 32);
-      if (t == 0) trace_ev(p, it, 3);
-      if (++s == p.stages) { s = 0; ph ^= 1; }
+      named_bar_arrive(1 + s, 32 + 32);
+      if (lane == 0) trace_ev(p, it, 3);
+      s += 4;
+      if (s >= p.stages) { s -= p.stages; ph ^= 1; }
     }
   } else {
-    setmaxnreg_inc<192>();
+    setmaxnreg_inc<176>();
     // ===================== epilogue: drain TMEM chains into fp32 registers =====================
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int a = (warp - 8) >> 2;      // 0: hi*hi^T accumulator, 1: hi*lo^T accumulator
@@ -287,7 +290,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const bool active = !(a == 1 && p.single_pass);
     for (int g = 0; g < ngroups; ++g) {
       const int b = g & 1;
-      mbar_wait_warp(&acc_full[b], (g >> 1) & 1);
+      mbar_wait_fast(&acc_full[b], (g >> 1) & 1);
       tc_fence_after();
       if (warp == 8 && lane == 0) trace_ev(p, g, 6);
       if (active) {
@@ -538,11 +541,12 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
       const int slack = (2 * nb < kTileRows) ? (kTileRows - 2 * nb) * 128 : 0;
       int st = (225 * 1024 - slack) / pl.stage_bytes;
       if (st > 14) st = 14;                            // named barrier ids 1..15
-      st &= ~1;                                        // even: the two MMA issuers alternate stages
+      if (st > 12) st = 12;
+      st &= ~3;                                        // multiple of 4: split warp w owns stages w, w+4, ...
       pl.stages = env_int("AFL_GRAM_STAGES", st);
       if (pl.stages > st) pl.stages = st;
-      if (pl.stages < 2) pl.stages = 2;
-      pl.stages &= ~1;
+      if (pl.stages < 4) pl.stages = 4;
+      pl.stages &= ~3;
     } else {
       pl.stage_bytes = 3 * kTileBytes;
       pl.stages = 4;
