@@ -83,7 +83,7 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
   const uint32_t bf_base = raw_base + kRawTiles * raw_bytes;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRawTiles; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < kRawTiles; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
     for (int s = 0; s < kBfStages; ++s) mbar_init(&bf_empty[s], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 2);
@@ -130,12 +130,12 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
         const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
         int it = it_begin + j;
         if (it < it_end) {
-          mbar_wait_warp(&acc_empty[b], gph ^ 1);
-          if (j == 1) mbar_wait_warp(&first_issued[b], gph);
+          mbar_wait_fast(&acc_empty[b], gph ^ 1);
+          if (j == 1) mbar_wait_fast(&first_issued[b], gph);
           tc_fence_after();
         }
         for (; it < it_end; it += 2) {
-          named_bar_sync(1 + s, 128 + 32);               // the converters have written and fenced stage s
+          named_bar_sync(1 + s, 32 + 32);                // converter warp s has written and fenced stage s
           tc_fence_after();
           const uint64_t dab = umma_desc_sw128(bf_base + static_cast<uint32_t>(s) * stage_bytes);
           if (elect_one()) {                             // A = rows 0..127 of the stage, B = rows 0..2nb-1
@@ -160,53 +160,56 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
     // Piece q = 32 aligned bytes of an fp32 tile = 8 values of row q/4.  TMA's 128-byte swizzle stored the
     // two 16-byte chunks of the piece swapped on odd rows; the bf16 chunk belongs at byte q*16 of the
     // 64-column half-row, i.e. at (row*128 + half*64 + (q%4)*16) XOR-swizzled by (row & 7).
-    const int t = threadIdx.x - 128;
+    // One converter warp per k-block (warp w owns k-blocks w, w+4, ... and bf16 stage w): four k-blocks are
+    // converted in parallel and a warp pays its barrier latencies once per k-block of its own.
+    const int w4 = warp - 4;
     const int npieces = p.nb * 4;                         // per fp32 tile
-    int rs = 0, bs = 0;                                   // raw ring slot of the first tile, bf16 stage
-    uint32_t rph = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait_warp(&bf_empty[bs], ((kb / kBfStages) & 1) ^ 1);
-      const uint32_t dst = bf_base + static_cast<uint32_t>(bs) * stage_bytes;
+    const uint32_t dst = bf_base + static_cast<uint32_t>(w4) * stage_bytes;
+    for (int kb = w4; kb < nkb; kb += kBfStages) {
+      mbar_wait_fast(&bf_empty[w4], ((kb / kBfStages) & 1) ^ 1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        mbar_wait_warp(&raw_full[rs], rph);
+        const int tile = 2 * kb + half;                   // position in the TMA stream
+        const int rs = tile % kRawTiles;
+        mbar_wait_fast(&raw_full[rs], (tile / kRawTiles) & 1);
         const uint32_t src = raw_base + static_cast<uint32_t>(rs) * raw_bytes;
-        float4 v0[4], v1[4];
+#pragma unroll 1
+        for (int q0 = 0; q0 < npieces; q0 += 4 * 32) {
+          float4 v0[4], v1[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {                     // all loads first (8 LDS.128 in flight)
-          const int q = t + u * 128;
-          if (q < npieces) { v0[u] = lds128(src + q * 32); v1[u] = lds128(src + q * 32 + 16); }
-        }
+          for (int u = 0; u < 4; ++u) {                   // all loads first (8 LDS.128 in flight)
+            const int q = q0 + u * 32 + lane;
+            if (q < npieces) { v0[u] = lds128(src + q * 32); v1[u] = lds128(src + q * 32 + 16); }
+          }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = t + u * 128;
-          if (q < npieces) {
-            const int row = q >> 2;
-            const bool odd = row & 1;
-            const float4 a = odd ? v1[u] : v0[u], b = odd ? v0[u] : v1[u];   // logical column order
-            const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            uint32_t h[4], l[4];
+          for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * 32 + lane;
+            if (q < npieces) {
+              const int row = q >> 2;
+              const bool odd = row & 1;
+              const float4 a = odd ? v1[u] : v0[u], b = odd ? v0[u] : v1[u];   // logical column order
+              const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+              uint32_t h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              h[e] = pack_bf16x2_rn(x[2 * e], x[2 * e + 1]);
-              const float r0 = x[2 * e] - __uint_as_float(h[e] << 16);
-              const float r1 = x[2 * e + 1] - __uint_as_float(h[e] & 0xFFFF0000u);
-              l[e] = pack_bf16x2_rn(r0, r1);
+              for (int e = 0; e < 4; ++e) {
+                h[e] = pack_bf16x2_rn(x[2 * e], x[2 * e + 1]);
+                const float r0 = x[2 * e] - __uint_as_float(h[e] << 16);
+                const float r1 = x[2 * e + 1] - __uint_as_float(h[e] & 0xFFFF0000u);
+                l[e] = pack_bf16x2_rn(r0, r1);
+              }
+              // logical 16-byte chunk of the bf16 row: c = half*4 + (stored pair index ^ ((row>>1)&3))
+              const int c = half * 4 + ((q & 3) ^ ((row >> 1) & 3));
+              const uint32_t off = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(c ^ (row & 7)) << 4);
+              sts128_u(dst + off, h[0], h[1], h[2], h[3]);
+              sts128_u(dst + static_cast<uint32_t>(p.nb) * 128u + off, l[0], l[1], l[2], l[3]);
             }
-            // logical 16-byte chunk of the bf16 row: c = half*4 + (stored pair index ^ ((row>>1)&3))
-            const int c = half * 4 + ((q & 3) ^ ((row >> 1) & 3));
-            const uint32_t off = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(c ^ (row & 7)) << 4);
-            sts128_u(dst + off, h[0], h[1], h[2], h[3]);
-            sts128_u(dst + static_cast<uint32_t>(p.nb) * 128u + off, l[0], l[1], l[2], l[3]);
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);       // this warp is done reading the fp32 tile
-        if (++rs == kRawTiles) { rs = 0; rph ^= 1; }
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);       // done reading this fp32 tile
       }
       fence_proxy_async_smem();
-      named_bar_arrive(1 + bs, 128 + 32);
-      if (++bs == kBfStages) bs = 0;
+      named_bar_arrive(1 + w4, 32 + 32);
     }
   } else {
     setmaxnreg_inc<168>();
@@ -218,7 +221,7 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
     for (int i = 0; i < 112; ++i) run[i] = 0.f;
     for (int g = 0; g < ngroups; ++g) {
       const int b = g & 1;
-      mbar_wait_warp(&acc_full[b], (g >> 1) & 1);
+      mbar_wait_fast(&acc_full[b], (g >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * 256 + a * p.nb);
 #pragma unroll
