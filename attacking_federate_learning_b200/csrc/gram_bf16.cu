@@ -41,6 +41,7 @@ struct B16Params {
   int kblocks;          // ceil(d / 64)
   int flush;            // k-blocks per TMEM accumulation chain (even)
   float* parts;         // [splits][2][128][128]
+  int kc_log2;          // consecutive k-blocks per CTA visit (contiguous 256 B << kc_log2 per row)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
@@ -75,7 +76,12 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wg = warp >> 2;
   const int split = blockIdx.x;
-  const int nkb = (p.kblocks - split + p.splits - 1) / p.splits;      // k-blocks split, split+splits, ...
+  // K assignment: chunks of (1 << kc_log2) consecutive k-blocks; CTA `split` owns chunks split, split+splits, ...
+  const int kc = 1 << p.kc_log2;
+  const int nchunks_total = (p.kblocks + kc - 1) >> p.kc_log2;
+  const int my_chunks = split < nchunks_total ? (nchunks_total - split + p.splits - 1) / p.splits : 0;
+  int nkb = my_chunks * kc;
+  if (my_chunks > 0 && split + (my_chunks - 1) * p.splits == nchunks_total - 1) nkb -= nchunks_total * kc - p.kblocks;
   const int ngroups = (nkb + p.flush - 1) / p.flush;
   const uint32_t raw_bytes = static_cast<uint32_t>(p.nb) * 128u;      // one fp32 tile [nb x 32]
   const uint32_t stage_bytes = static_cast<uint32_t>(p.nb) * 256u;    // b1 (nb rows) || b2 (nb rows)
@@ -113,7 +119,8 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
         for (int it = 0; it < 2 * nkb; ++it) {
           mbar_wait(&raw_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
-          const int kb = split + (it >> 1) * p.splits;
+          const int i = it >> 1;                            // k-block index in this CTA's stream
+          const int kb = ((split + (i >> p.kc_log2) * p.splits) << p.kc_log2) + (i & (kc - 1));
           tma_load_2d(smem + static_cast<size_t>(s) * raw_bytes, &tmap, &raw_full[s], kb * kB16Cols + (it & 1) * 32, 0, pol);
           if (++s == kRawTiles) { s = 0; ph ^= 1; }
         }
@@ -283,10 +290,12 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
   }
   B16Params p{};
   p.n = n; p.nb = (n + 15) & ~15;
-  p.splits = splits;
   p.kblocks = static_cast<int>((d + kB16Cols - 1) / kB16Cols);
   p.flush = flush < 2 ? 2 : (flush & ~1);
+  p.splits = splits;
   p.parts = parts;
+  p.kc_log2 = 0;
+  if (const char* e = getenv("AFL_GRAM_KCHUNK_LOG2")) { p.kc_log2 = atoi(e); if (p.kc_log2 < 0 || p.kc_log2 > 4) p.kc_log2 = 0; }
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};

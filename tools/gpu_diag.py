@@ -285,6 +285,10 @@ for fl in ["8","32","512"]:
     reg(f"b16_fl{fl}", case_gram, 100, 11_200_000, F["TC"], f"b16_fl{fl}", True, env={"AFL_GRAM_FLUSH": fl})
 for dbg in ["1","2"]:
     reg(f"c2_dbg{dbg}", case_gram, 100, 11_200_000, F["TC"], f"c2_dbg{dbg}", True, env={"AFL_GRAM_DBG": dbg})
+for kc in ["1","2","3"]:
+    reg(f"b16_kc{kc}", case_gram, 100, 11_200_000, F["TC"] | 32, f"b16_kc{kc}", True, env={"AFL_GRAM_KCHUNK_LOG2": kc})
+reg("b16_ragged32", case_gram, 100, 100_004, F["TC"] | 32, "b16_ragged32")
+reg("b16_n64_32", case_gram, 64, 65_540, F["TC"] | 32, "b16_n64_32")
 reg("n500_gram", case_gram, 500, 1 << 20, F["TC"], "n500", True)
 reg("n1000_gram", case_gram, 1000, 1 << 19, F["TC"], "n1000", True)
 reg("select_10", case_select, 10, 2, 0)
