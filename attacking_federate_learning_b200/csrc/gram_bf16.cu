@@ -6,13 +6,15 @@
 // gram.cu needs >= 620 tensor cycles per 32 columns, more than the ~550 cycles HBM needs for them, while
 // bf16 operands need 310.  Here:
 //
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, zero OOB fill) streams fp32 tiles [N_pad x 32] into
-//     a deep ring (8 tiles in flight per SM) — deep asynchronous prefetch without registers;
-//   * 4 converter warps turn two fp32 tiles into one bf16 operand stage: every value is split into two
-//     bf16 terms, g = b1 + b2 + r (both roundings to nearest, |r| <= 2^-17 |g|), stored as b1 || b2,
-//     K-major, 64 columns per 128-byte row, SWIZZLE_128B.  A 32-byte piece of the fp32 tile maps to the
-//     16-byte chunk at HALF its byte offset (the two swizzles cancel), so no address math is needed
-//     beyond swapping the two halves on odd rows;
+//   * TMA (cp.async.bulk.tensor.2d, no swizzle, zero OOB fill) streams one k-block [N x 64] of fp32 per
+//     instruction into a 4-slot ring.  tools/tma_bench.cu measured a fixed ~450 ns per 2-D box per SM
+//     whatever its size (25..100 rows, 128..512 B rows), so 128-byte-wide boxes cap at 3.8 TB/s chip-wide
+//     while 256-byte-wide boxes reach the HBM bound; the raw layout is free because only the converters
+//     read it;
+//   * 4 converter warps (one per ring slot / operand stage) turn the fp32 k-block into one bf16 operand
+//     stage: every value is split into two bf16 terms, g = b1 + b2 + r (both roundings to nearest,
+//     |r| <= 2^-17 |g|), stored as b1 || b2, K-major, 64 columns per 128-byte row, SWIZZLE_128B.  A half
+//     warp reads one 256-byte fp32 row and writes one 128-byte bf16 row of b1 and of b2 (conflict-free);
 //   * S ~= b1 b1^T + b1 b2^T + (b1 b2^T)^T: ONE tcgen05.mma.kind::f16 (K = 16) per 16 columns with
 //     A = b1 (M = 128) and B = b1 || b2 (N = 2*N_pad), fp32 accumulation in TMEM.  Dropped terms
 //     (b2 b2^T, r) are ~2^-17 relative per product; b2 b2^T is positive on every squared distance and
@@ -30,7 +32,7 @@ namespace afl {
 namespace gram {
 
 constexpr int kB16Threads = 512;
-constexpr int kRawTiles = 8;         // fp32 tiles [nb x 32 cols] in flight (TMA ring)
+constexpr int kRawSlots = 4;         // fp32 k-blocks [n x 64 cols] in the TMA ring (slot = k-block % 4)
 constexpr int kBfStages = 4;         // bf16 operand stages [2*nb rows x 64 cols]
 constexpr int kB16Cols = 64;         // fp32 columns per k-block = 128 bytes of bf16 per row
 constexpr int kB16PartElems = 2 * 128 * 128;
@@ -41,7 +43,6 @@ struct B16Params {
   int kblocks;          // ceil(d / 64)
   int flush;            // k-blocks per TMEM accumulation chain (even)
   float* parts;         // [splits][2][128][128]
-  int kc_log2;          // consecutive k-blocks per CTA visit (contiguous 256 B << kc_log2 per row)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
@@ -51,6 +52,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
 }
 __device__ __forceinline__ void sts128_u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts64_u(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -70,26 +74,21 @@ __global__ void __launch_bounds__(kB16Threads, 1)
 gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t raw_full[kRawTiles], raw_empty[kRawTiles], bf_empty[kBfStages], acc_full[2],
+  __shared__ __align__(8) uint64_t raw_full[kRawSlots], raw_empty[kRawSlots], bf_empty[kBfStages], acc_full[2],
       acc_empty[2], first_issued[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wg = warp >> 2;
   const int split = blockIdx.x;
-  // K assignment: chunks of (1 << kc_log2) consecutive k-blocks; CTA `split` owns chunks split, split+splits, ...
-  const int kc = 1 << p.kc_log2;
-  const int nchunks_total = (p.kblocks + kc - 1) >> p.kc_log2;
-  const int my_chunks = split < nchunks_total ? (nchunks_total - split + p.splits - 1) / p.splits : 0;
-  int nkb = my_chunks * kc;
-  if (my_chunks > 0 && split + (my_chunks - 1) * p.splits == nchunks_total - 1) nkb -= nchunks_total * kc - p.kblocks;
+  const int nkb = (p.kblocks - split + p.splits - 1) / p.splits;      // k-blocks split, split+splits, ...
   const int ngroups = (nkb + p.flush - 1) / p.flush;
-  const uint32_t raw_bytes = static_cast<uint32_t>(p.nb) * 128u;      // one fp32 tile [nb x 32]
+  const uint32_t raw_bytes = static_cast<uint32_t>(p.n) * 256u;       // one fp32 k-block [n x 64], row-major
   const uint32_t stage_bytes = static_cast<uint32_t>(p.nb) * 256u;    // b1 (nb rows) || b2 (nb rows)
   const uint32_t raw_base = smem_u32(smem);
-  const uint32_t bf_base = raw_base + kRawTiles * raw_bytes;
+  const uint32_t bf_base = (raw_base + kRawSlots * raw_bytes + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRawTiles; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
+    for (int s = 0; s < kRawSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
     for (int s = 0; s < kBfStages; ++s) mbar_init(&bf_empty[s], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 2);
@@ -111,18 +110,16 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
   if (wg == 0) {
     setmaxnreg_dec<64>();
     if (warp == 0) {
-      // ===================== TMA producer: 2 fp32 tiles (32 columns each) per k-block =====================
+      // ===================== TMA producer: one box [n x 64 fp32] per k-block =====================
       if (lane == 0) {
         const uint64_t pol = policy_evict_first();
         int s = 0;
         uint32_t ph = 0;
-        for (int it = 0; it < 2 * nkb; ++it) {
+        for (int i = 0; i < nkb; ++i) {
           mbar_wait(&raw_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
-          const int i = it >> 1;                            // k-block index in this CTA's stream
-          const int kb = ((split + (i >> p.kc_log2) * p.splits) << p.kc_log2) + (i & (kc - 1));
-          tma_load_2d(smem + static_cast<size_t>(s) * raw_bytes, &tmap, &raw_full[s], kb * kB16Cols + (it & 1) * 32, 0, pol);
-          if (++s == kRawTiles) { s = 0; ph ^= 1; }
+          tma_load_2d(smem + static_cast<size_t>(s) * raw_bytes, &tmap, &raw_full[s], (split + i * p.splits) * kB16Cols, 0, pol);
+          if (++s == kRawSlots) { s = 0; ph ^= 1; }
         }
       }
     } else if (warp == 1 || warp == 3) {
@@ -163,58 +160,48 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
     }
   } else if (wg == 1) {
     setmaxnreg_dec<112>();
-    // ===================== converters: two fp32 tiles -> one bf16 stage b1 || b2 =====================
-    // Piece q = 32 aligned bytes of an fp32 tile = 8 values of row q/4.  TMA's 128-byte swizzle stored the
-    // two 16-byte chunks of the piece swapped on odd rows; the bf16 chunk belongs at byte q*16 of the
-    // 64-column half-row, i.e. at (row*128 + half*64 + (q%4)*16) XOR-swizzled by (row & 7).
-    // One converter warp per k-block (warp w owns k-blocks w, w+4, ... and bf16 stage w): four k-blocks are
-    // converted in parallel and a warp pays its barrier latencies once per k-block of its own.
+    // ===================== converters: one fp32 k-block -> one bf16 stage b1 || b2 =====================
+    // Converter warp w owns ring slot w, operand stage w and k-blocks w, w+4, ...: four k-blocks are
+    // converted in parallel.  A half warp takes one fp32 row (16 lanes x 16 bytes = 64 columns): the lane
+    // with fp32 chunk c16 owns bf16 bytes [8*c16, 8*c16+8) of the 128-byte bf16 row, i.e. half of the
+    // 16-byte chunk c16/2, which SWIZZLE_128B places at chunk (c16/2) ^ (row & 7).
     const int w4 = warp - 4;
-    const int npieces = p.nb * 4;                         // per fp32 tile
+    const uint32_t src = raw_base + static_cast<uint32_t>(w4) * raw_bytes;
     const uint32_t dst = bf_base + static_cast<uint32_t>(w4) * stage_bytes;
+    const uint32_t dst2 = dst + static_cast<uint32_t>(p.nb) * 128u;
+    for (int i = lane; i < (p.nb - p.n) * 8; i += 32) {   // pad rows n..nb-1 stay zero for the whole kernel
+      const uint32_t off = static_cast<uint32_t>(p.n) * 128u + static_cast<uint32_t>(i) * 16u;
+      sts128_u(dst + off, 0u, 0u, 0u, 0u);
+      sts128_u(dst2 + off, 0u, 0u, 0u, 0u);
+    }
+    const int rsub = lane >> 4, c16 = lane & 15;
+    const uint32_t src_lane = src + static_cast<uint32_t>(rsub) * 256u + static_cast<uint32_t>(c16) * 16u;
     for (int kb = w4; kb < nkb; kb += kBfStages) {
-      mbar_wait_fast(&bf_empty[w4], ((kb / kBfStages) & 1) ^ 1);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int tile = 2 * kb + half;                   // position in the TMA stream
-        const int rs = tile % kRawTiles;
-        mbar_wait_fast(&raw_full[rs], (tile / kRawTiles) & 1);
-        const uint32_t src = raw_base + static_cast<uint32_t>(rs) * raw_bytes;
+      const uint32_t ph = static_cast<uint32_t>(kb / kBfStages) & 1u;
+      mbar_wait_fast(&bf_empty[w4], ph ^ 1);
+      mbar_wait_fast(&raw_full[w4], ph);
 #pragma unroll 1
-        for (int q0 = 0; q0 < npieces; q0 += 4 * 32) {
-          float4 v0[4], v1[4];
+      for (int r0 = 0; r0 < p.n; r0 += 16) {
+        float4 v[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {                   // all loads first (8 LDS.128 in flight)
-            const int q = q0 + u * 32 + lane;
-            if (q < npieces) { v0[u] = lds128(src + q * 32); v1[u] = lds128(src + q * 32 + 16); }
-          }
+        for (int u = 0; u < 8; ++u)                       // all loads first (8 LDS.128 in flight)
+          if (r0 + 2 * u + rsub < p.n) v[u] = lds128(src_lane + static_cast<uint32_t>(r0 + 2 * u) * 256u);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int q = q0 + u * 32 + lane;
-            if (q < npieces) {
-              const int row = q >> 2;
-              const bool odd = row & 1;
-              const float4 a = odd ? v1[u] : v0[u], b = odd ? v0[u] : v1[u];   // logical column order
-              const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-              uint32_t h[4], l[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                h[e] = pack_bf16x2_rn(x[2 * e], x[2 * e + 1]);
-                const float r0 = x[2 * e] - __uint_as_float(h[e] << 16);
-                const float r1 = x[2 * e + 1] - __uint_as_float(h[e] & 0xFFFF0000u);
-                l[e] = pack_bf16x2_rn(r0, r1);
-              }
-              // logical 16-byte chunk of the bf16 row: c = half*4 + (stored pair index ^ ((row>>1)&3))
-              const int c = half * 4 + ((q & 3) ^ ((row >> 1) & 3));
-              const uint32_t off = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(c ^ (row & 7)) << 4);
-              sts128_u(dst + off, h[0], h[1], h[2], h[3]);
-              sts128_u(dst + static_cast<uint32_t>(p.nb) * 128u + off, l[0], l[1], l[2], l[3]);
-            }
+        for (int u = 0; u < 8; ++u) {
+          const int row = r0 + 2 * u + rsub;
+          if (row < p.n) {
+            const uint32_t h0 = pack_bf16x2_rn(v[u].x, v[u].y), h1 = pack_bf16x2_rn(v[u].z, v[u].w);
+            const uint32_t l0 = pack_bf16x2_rn(v[u].x - __uint_as_float(h0 << 16), v[u].y - __uint_as_float(h0 & 0xFFFF0000u));
+            const uint32_t l1 = pack_bf16x2_rn(v[u].z - __uint_as_float(h1 << 16), v[u].w - __uint_as_float(h1 & 0xFFFF0000u));
+            const uint32_t off = static_cast<uint32_t>(row) * 128u +
+                                 (static_cast<uint32_t>((c16 >> 1) ^ (row & 7)) << 4) + (static_cast<uint32_t>(c16 & 1) << 3);
+            sts64_u(dst + off, h0, h1);
+            sts64_u(dst2 + off, l0, l1);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);       // done reading this fp32 tile
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[w4]);         // done reading this ring slot
       fence_proxy_async_smem();
       named_bar_arrive(1 + w4, 32 + 32);
     }
@@ -294,18 +281,16 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
   p.flush = flush < 2 ? 2 : (flush & ~1);
   p.splits = splits;
   p.parts = parts;
-  p.kc_log2 = 0;
-  if (const char* e = getenv("AFL_GRAM_KCHUNK_LOG2")) { p.kc_log2 = atoi(e); if (p.kc_log2 < 0 || p.kc_log2 > 4) p.kc_log2 = 0; }
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
-  const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(p.nb)};
+  const cuuint32_t box[2] = {kB16Cols, static_cast<cuuint32_t>(n)};
   const cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(G), gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", static_cast<int>(r)); return AFL_ERR_CUDA; }
-  const size_t smem = static_cast<size_t>(kRawTiles) * p.nb * 128 + static_cast<size_t>(kBfStages) * p.nb * 256 + 1024;
+  const size_t smem = static_cast<size_t>(kRawSlots) * n * 256 + static_cast<size_t>(kBfStages) * p.nb * 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     AFL_CUDA(cudaFuncSetAttribute(gram_bf16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

@@ -274,6 +274,9 @@ reg("b16_n64", case_gram, 64, 65_540, F["TC"], "b16_n64")
 reg("b16_n112", case_gram, 112, 200_000, F["TC"], "b16_n112")
 reg("b16_n70", case_gram, 70, 1_000_000, F["TC"], "b16_n70", True)
 reg("b16_ident", case_gram_identical, 100, 70_000, F["TC"])
+reg("b16_ident32", case_gram_identical, 100, 70_004, F["TC"] | 32)
+reg("b16_n112", case_gram, 112, 65_540, F["TC"] | 32, "b16_n112")
+reg("b16_n97", case_gram, 97, 40_000, F["TC"] | 32, "b16_n97")
 for sp in ["37","74"]:
     reg(f"b16_sp{sp}", case_gram, 100, 11_200_000, F["TC"], f"b16_sp{sp}", True, env={"AFL_GRAM_SPLITS": sp})
 reg("b16_flush2", case_gram, 100, 11_200_000, F["TC"], "b16_flush2", True, env={"AFL_GRAM_FLUSH": "2"})
