@@ -112,11 +112,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 21)) {
-      printf("afl: mbarrier timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, (void*)bar, parity);
+    if (clock64() - t0 > (1ll << 32)) {                  // ~2 s: no legitimate wait is longer than one pipeline step
+      printf("afl: mbarrier timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar), parity);
       __trap();
     }
   }

@@ -510,10 +510,11 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
   if (pl.tensor) {
     pl.tiles = (n + kTileRows - 1) / kTileRows;
     const char* kenv = getenv("AFL_GRAM_KERNEL");
-    // default: TMA + split-TF32 (measured faster and less biased today); the bf16x2 kernel has the
-    // tensor headroom (310 vs 620 cycles per 32 columns) and is selected by flag or AFL_GRAM_KERNEL=bf16
+    // Streaming shapes (64 <= N_pad <= 112, D >= 32768) default to the bf16x2 kernel (gram_bf16.cu: twice the
+    // tensor headroom and a loader that is not capped by the TMA box rate); AFL_GRAM_TF32X2 or
+    // AFL_GRAM_KERNEL=tf32 keeps the TMA + split-TF32 kernel (smaller uniform bias, ~0.9e-6 vs ~3.2e-6).
     pl.bf16 = bf16x2_eligible(n, d) && !(flags & (AFL_GRAM_SINGLE_PASS | AFL_GRAM_TF32X2)) &&
-              ((flags & AFL_GRAM_BF16X2) || (kenv && kenv[0] == 'b'));
+              !(kenv && kenv[0] == 't');
     const int pairs = pl.tiles * pl.tiles;
     int kc_log2 = env_int("AFL_GRAM_KCHUNK_LOG2", 0);
     if (kc_log2 < 0 || kc_log2 > 4) kc_log2 = 0;

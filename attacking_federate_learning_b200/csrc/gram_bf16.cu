@@ -176,25 +176,57 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
     }
     const int rsub = lane >> 4, c16 = lane & 15;
     const uint32_t src_lane = src + static_cast<uint32_t>(rsub) * 256u + static_cast<uint32_t>(c16) * 16u;
+    // Row r0 + 2u + rsub (r0 a multiple of 16): the swizzle term only depends on (2u + rsub) & 7, so the
+    // destination offset is r0*128 + u*256 + one of four per-lane constants.
+    uint32_t lane_off[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      lane_off[k] = static_cast<uint32_t>(rsub) * 128u + (static_cast<uint32_t>(c16 & 1) << 3) +
+                    (static_cast<uint32_t>((c16 >> 1) ^ ((2 * k + rsub) & 7)) << 4);
+    const int full_rows = p.n & ~15;
     for (int kb = w4; kb < nkb; kb += kBfStages) {
       const uint32_t ph = static_cast<uint32_t>(kb / kBfStages) & 1u;
       mbar_wait_fast(&bf_empty[w4], ph ^ 1);
       mbar_wait_fast(&raw_full[w4], ph);
-#pragma unroll 1
-      for (int r0 = 0; r0 < p.n; r0 += 16) {
-        float4 v[8];
+      // Full 16-row groups, branch-free and software-pipelined: the next group's 8 LDS.128 are issued
+      // before this group's 16 STS.64, the 8 independent conversion chains interleave.
+      float4 v[8];
+      if (full_rows > 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u)                       // all loads first (8 LDS.128 in flight)
-          if (r0 + 2 * u + rsub < p.n) v[u] = lds128(src_lane + static_cast<uint32_t>(r0 + 2 * u) * 256u);
+        for (int u = 0; u < 8; ++u) v[u] = lds128(src_lane + static_cast<uint32_t>(2 * u) * 256u);
+      }
+#pragma unroll 1
+      for (int r0 = 0; r0 < full_rows; r0 += 16) {
+        uint32_t h[8][2], l[8][2];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int row = r0 + 2 * u + rsub;
+          h[u][0] = pack_bf16x2_rn(v[u].x, v[u].y);
+          h[u][1] = pack_bf16x2_rn(v[u].z, v[u].w);
+          l[u][0] = pack_bf16x2_rn(v[u].x - __uint_as_float(h[u][0] << 16), v[u].y - __uint_as_float(h[u][0] & 0xFFFF0000u));
+          l[u][1] = pack_bf16x2_rn(v[u].z - __uint_as_float(h[u][1] << 16), v[u].w - __uint_as_float(h[u][1] & 0xFFFF0000u));
+        }
+        if (r0 + 16 < full_rows) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = lds128(src_lane + static_cast<uint32_t>(r0 + 16 + 2 * u) * 256u);
+        }
+        const uint32_t o0 = static_cast<uint32_t>(r0) * 128u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t off = o0 + static_cast<uint32_t>(u) * 256u + lane_off[u & 3];
+          sts64_u(dst + off, h[u][0], h[u][1]);
+          sts64_u(dst2 + off, l[u][0], l[u][1]);
+        }
+      }
+      if (full_rows < p.n) {                              // ragged tail (n % 16 rows), predicated per row
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int row = full_rows + 2 * u + rsub;
           if (row < p.n) {
-            const uint32_t h0 = pack_bf16x2_rn(v[u].x, v[u].y), h1 = pack_bf16x2_rn(v[u].z, v[u].w);
-            const uint32_t l0 = pack_bf16x2_rn(v[u].x - __uint_as_float(h0 << 16), v[u].y - __uint_as_float(h0 & 0xFFFF0000u));
-            const uint32_t l1 = pack_bf16x2_rn(v[u].z - __uint_as_float(h1 << 16), v[u].w - __uint_as_float(h1 & 0xFFFF0000u));
-            const uint32_t off = static_cast<uint32_t>(row) * 128u +
-                                 (static_cast<uint32_t>((c16 >> 1) ^ (row & 7)) << 4) + (static_cast<uint32_t>(c16 & 1) << 3);
+            const float4 t = lds128(src_lane + static_cast<uint32_t>(full_rows + 2 * u) * 256u);
+            const uint32_t h0 = pack_bf16x2_rn(t.x, t.y), h1 = pack_bf16x2_rn(t.z, t.w);
+            const uint32_t l0 = pack_bf16x2_rn(t.x - __uint_as_float(h0 << 16), t.y - __uint_as_float(h0 & 0xFFFF0000u));
+            const uint32_t l1 = pack_bf16x2_rn(t.z - __uint_as_float(h1 << 16), t.w - __uint_as_float(h1 & 0xFFFF0000u));
+            const uint32_t off = static_cast<uint32_t>(full_rows) * 128u + static_cast<uint32_t>(u) * 256u + lane_off[u & 3];
             sts64_u(dst + off, h0, h1);
             sts64_u(dst2 + off, l0, l1);
           }

@@ -53,8 +53,8 @@ enum {
   AFL_GRAM_FORCE_SIMT = 1,    /* CUDA-core difference kernel (verification / unaligned pitch)      */
   AFL_GRAM_FORCE_TCGEN05 = 2, /* fail with AFL_ERR_UNSUPPORTED instead of falling back to SIMT     */
   AFL_GRAM_SINGLE_PASS = 4,   /* tcgen05: hi*hi only (plain TF32), for measurement                  */
-  AFL_GRAM_TF32X2 = 16,       /* tcgen05: always the TMA + split-TF32 kernel (the default)                     */
-  AFL_GRAM_BF16X2 = 32,       /* tcgen05: bf16x2 kernel (gram_bf16.cu) when eligible: 64<=N_pad<=112, D>=32768 */
+  AFL_GRAM_TF32X2 = 16,       /* tcgen05: always the TMA + split-TF32 kernel (default outside the bf16x2 range) */
+  AFL_GRAM_BF16X2 = 32,       /* tcgen05: bf16x2 kernel (gram_bf16.cu), the default when 64<=N_pad<=112, D>=32768 */
   AFL_GRAM_REWRITE_HI = 8     /* accepted, ignored (kind::tf32 was measured to ignore the low 13     */
                               /* mantissa bits of fp32 operands, which is what the split relies on)  */
 };

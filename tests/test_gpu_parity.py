@@ -137,7 +137,7 @@ def test_krum_matches_oracle(api, n, d, f, seed):
     Gp = torch.zeros((n, (d + 3) // 4 * 4), device="cuda")[:, :d]; Gp.copy_(Gd)
     off = ~np.eye(n, dtype=bool)
     ref2 = (table64 ** 2)[off]
-    for flags, bias_cap in ((nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2, 6e-6), (nat.GRAM_FORCE_TCGEN05, 2e-6)):
+    for flags, bias_cap in ((nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2, 6e-6), (nat.GRAM_FORCE_TCGEN05 | nat.GRAM_TF32X2, 2e-6)):
         d2 = dev.sqdist_partial(Gp, flags).cpu().numpy()
         rel = (d2[off] - ref2) / ref2
         assert np.abs(rel).max() < bias_cap, np.abs(rel).max()
@@ -154,7 +154,8 @@ def test_identical_rows_tie_goes_to_user_1(api):
     n, d, f = 80, 40960, 19                               # large enough for the bf16x2 kernel to be eligible
     G = 5.0 * hetero(rng, n, d); G[:f] = 0.002 * G[f]
     Gd = torch.from_numpy(G).cuda()
-    for flags in (nat.GRAM_FORCE_TCGEN05, nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2, nat.GRAM_FORCE_SIMT):
+    for flags in (nat.GRAM_FORCE_TCGEN05 | nat.GRAM_TF32X2, nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2, 0,
+                  nat.GRAM_FORCE_SIMT):
         d2 = dev.sqdist_partial(Gd, flags)
         assert float(d2[:f, :f].abs().max()) == 0.0
         dist = dev.sqdist_to_dist(d2)

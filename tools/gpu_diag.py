@@ -271,10 +271,17 @@ reg("b16_c2", case_gram, 100, 11_200_000, F["TC"] | 32, "b16_c2", True)
 reg("tf32_c2", case_gram, 100, 11_200_000, F["TC"] | 16, "tf32_c2", True)
 reg("b16_ragged", case_gram, 100, 100_004, F["TC"], "b16_ragged")
 reg("b16_n64", case_gram, 64, 65_540, F["TC"], "b16_n64")
+reg("b16_n100_200k", case_gram, 100, 200_000, F["TC"] | 32, "b16_n100_200k")
+reg("b16_n100_2m", case_gram, 100, 2_000_000, F["TC"] | 32, "b16_n100_2m")
+reg("b16_n80_2m", case_gram, 80, 2_000_000, F["TC"] | 32, "b16_n80_2m")
 reg("b16_n112", case_gram, 112, 200_000, F["TC"], "b16_n112")
 reg("b16_n70", case_gram, 70, 1_000_000, F["TC"], "b16_n70", True)
 reg("b16_ident", case_gram_identical, 100, 70_000, F["TC"])
+reg("c2_tf32", case_gram, 100, 11_200_000, F["TC"] | 16, "c2_tf32", True)
 reg("b16_ident32", case_gram_identical, 100, 70_004, F["TC"] | 32)
+reg("b16_n100_200k", case_gram, 100, 200_000, F["TC"] | 32, "b16_n100_200k")
+reg("b16_n100_2m", case_gram, 100, 2_000_000, F["TC"] | 32, "b16_n100_2m")
+reg("b16_n80_2m", case_gram, 80, 2_000_000, F["TC"] | 32, "b16_n80_2m")
 reg("b16_n112", case_gram, 112, 65_540, F["TC"] | 32, "b16_n112")
 reg("b16_n97", case_gram, 97, 40_000, F["TC"] | 32, "b16_n97")
 for sp in ["37","74"]:
