@@ -144,6 +144,21 @@ def alie(G_mal: torch.Tensor, z: float, bcast: torch.Tensor | None = None, alias
     return crafted, mu, sigma
 
 
+def alie_band(mu: torch.Tensor, sigma: torch.Tensor, z: float, x: torch.Tensor | None = None,
+              out: torch.Tensor | None = None):
+    """x is None: mu - z*sigma (malicious.py:35); else np.clip(x, mu - z*sigma, mu + z*sigma) (backdoor.py:60-61)."""
+    d = mu.numel()
+    for t in (mu, sigma) + (() if x is None else (x,)):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == d):
+            raise ValueError("alie_band: contiguous float32 CUDA vectors of equal length expected")
+    if out is None:
+        out = torch.empty(d, dtype=torch.float32, device=mu.device)
+    with torch.cuda.device(mu.device):
+        nat.check(nat.lib().afl_alie_band(mu.data_ptr(), sigma.data_ptr(), float(z),
+                                          None if x is None else x.data_ptr(), out.data_ptr(), d, _stream_ptr(mu)))
+    return out
+
+
 def momentum_step(weights: torch.Tensor, velocity: torch.Tensor, grads: torch.Tensor, momentum: float, lr: float):
     d = weights.numel()
     with torch.cuda.device(weights.device):

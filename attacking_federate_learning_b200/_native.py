@@ -37,6 +37,7 @@ SIGNATURES = {
     "afl_trimmed_mean": (_i, [_vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp]),
     "afl_gather_row": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),
     "afl_alie": (_i, [_vp, _i, _i64, _i64, _i, _d, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "afl_alie_band": (_i, [_vp, _vp, _d, _vp, _vp, _i64, _vp]),
     "afl_momentum_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _vp]),
     "afl_defend_host": (_i, [C.c_char_p, _vp, _i, _i64, _i64, _i, _i, _vp, C.POINTER(_i), _i64]),
 }

@@ -103,6 +103,7 @@ int alie(const void* G, int f, int64_t d, int64_t ld, int dtype, double z, float
 int gather_row(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* idx_dev, float* out,
                cudaStream_t stream);
 int momentum_step(float* w, float* v, const float* g, int64_t d, float momentum, float lr, cudaStream_t stream);
+int alie_band(const float* mu, const float* sigma, double z, const float* x, float* out, int64_t d, cudaStream_t stream);
 }
 
 __global__ void add_f64_kernel(double* __restrict__ acc, const double* __restrict__ x, size_t n, int first) {
@@ -322,6 +323,10 @@ int afl_alie(const void* G_mal, int f, int64_t d, int64_t ld, int dtype, double 
              float* crafted_out, float* bcast_rows, int64_t bcast_ld, void* stream) {
   return colstats::alie(G_mal, f, d, ld, dtype, z, mu_out, sigma_out, crafted_out, bcast_rows, bcast_ld,
                         static_cast<cudaStream_t>(stream));
+}
+
+int afl_alie_band(const float* mu, const float* sigma, double z, const float* x, float* out, int64_t d, void* stream) {
+  return colstats::alie_band(mu, sigma, z, x, out, d, static_cast<cudaStream_t>(stream));
 }
 
 int afl_momentum_step(float* weights, float* velocity, const float* grads, int64_t d, float momentum,

@@ -148,6 +148,25 @@ momentum_kernel(float* __restrict__ w, float* __restrict__ v, const float* __res
   }
 }
 
+// ALIE band: lo = mu - z*sigma, hi = mu + z*sigma (fp32 product, fp32 sum: the roundings of
+// `grads_mean -/+ num_std * grads_stdev`).  x == nullptr: out = lo (malicious.py:35, DriftAttack);
+// otherwise out = np.clip(x, lo, hi) = minimum(maximum(x, lo), hi) with NumPy's NaN propagation
+// (backdoor.py:60-61).  out may alias mu or x (each element is read before it is written).
+__global__ void __launch_bounds__(kBlock)
+band_kernel(const float* mu, const float* sigma, float z, const float* x, float* out, int64_t d) {
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; c < d;
+       c += static_cast<int64_t>(gridDim.x) * kBlock) {
+    const float m = mu[c], zs = __fmul_rn(z, sigma[c]);
+    const float lo = __fsub_rn(m, zs);
+    if (x == nullptr) { out[c] = lo; continue; }
+    const float hi = __fadd_rn(m, zs);
+    const float v = x[c];
+    float r = fminf(fmaxf(v, lo), hi);
+    if (v != v || lo != lo || hi != hi) r = __int_as_float(0x7fc00000);
+    out[c] = r;
+  }
+}
+
 static bool vec_ok(const void* G, int64_t ld, int dtype) {
   const int64_t es = dtype == AFL_F32 ? 4 : 2;
   return (reinterpret_cast<uintptr_t>(G) % 16 == 0) && ((ld * es) % 16 == 0);
@@ -211,6 +230,16 @@ int momentum_step(float* w, float* v, const float* g, int64_t d, float momentum,
   if (blocks > 148 * 16) blocks = 148 * 16;
   momentum_kernel<<<static_cast<unsigned>(blocks), kBlock, 0, stream>>>(w, v, g, d, momentum, lr);
   AFL_LAUNCH_CHECK("momentum_kernel");
+  return AFL_OK;
+}
+
+int alie_band(const float* mu, const float* sigma, double z, const float* x, float* out, int64_t d,
+              cudaStream_t stream) {
+  if (!mu || !sigma || !out || d < 1) { set_error("afl_alie_band: bad argument"); return AFL_ERR_BAD_ARG; }
+  int64_t blocks = ceil_div64(d, kBlock);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  band_kernel<<<static_cast<unsigned>(blocks), kBlock, 0, stream>>>(mu, sigma, static_cast<float>(z), x, out, d);
+  AFL_LAUNCH_CHECK("band_kernel");
   return AFL_OK;
 }
 

@@ -134,6 +134,15 @@ int afl_gather_row(const void* G, int n, int64_t d, int64_t ld, int dtype, const
 int afl_alie(const void* G_mal, int f, int64_t d, int64_t ld, int dtype, double z, float* mu_out,
              float* sigma_out, float* crafted_out, float* bcast_rows, int64_t bcast_ld, void* stream);
 
+/* ---- ALIE band:  malicious.py:35 (x == NULL)  and  backdoor.py:60-61 (x != NULL) --------------
+ * lo = mu - z*sigma, hi = mu + z*sigma in fp32 (the roundings of `grads_mean -/+ num_std*grads_stdev`).
+ * x == NULL: out = lo, DriftAttack._attack_grads on statistics that already exist on the device.
+ * x != NULL: out = np.clip(x, lo, hi) (NaN propagates as in NumPy), the clamp BackdoorAttack applies to
+ * the gradient its maliciously trained network asks for.  fp32 device vectors of length d; out may
+ * alias mu or x. */
+int afl_alie_band(const float* mu, const float* sigma, double z, const float* x, float* out, int64_t d,
+                  void* stream);
+
 /* ---- server momentum step:  server.py:89-90 ----------------------------------------------------
  * v = momentum*v - lr*g ;  w += v   (fp32, in place). */
 int afl_momentum_step(float* weights, float* velocity, const float* grads, int64_t d, float momentum,

@@ -244,6 +244,18 @@ def alie_attack(rows, num_std: float):
     return mu, mu, sigma
 
 
+def backdoor_attack_grads(grads_mean, grads_stdev, original_params, learning_rate: float, num_std: float,
+                          train_malicious_network):
+    """backdoor.py:52-65 (BackdoorAttack._attack_grads); `train_malicious_network` stands for
+    backdoor.py:108 (model training, outside the aggregation path)."""
+    initial_params_flat = original_params - learning_rate * grads_mean                    # backdoor.py:54
+    mal_net_params = train_malicious_network(initial_params_flat)                          # backdoor.py:56
+    new_params = mal_net_params + learning_rate * grads_mean                              # backdoor.py:59
+    new_grads = (initial_params_flat - new_params) / learning_rate                        # backdoor.py:60
+    return np.clip(new_grads, grads_mean - num_std * grads_stdev,                         # backdoor.py:62-63
+                   grads_mean + num_std * grads_stdev)
+
+
 def momentum_step(weights, velocity, grads, momentum: float, learning_rate: float):
     """server.py:89-90:  v = momentum*v - lr*g ;  w += v   (returns new (w, v), fp32)."""
     velocity = momentum * velocity - learning_rate * grads

@@ -20,6 +20,11 @@ def golden():
     return data
 
 
+@pytest.fixture(scope="session")
+def golden_backdoor():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_backdoor_v1.npz"), allow_pickle=False)
+
+
 def golden_names(kind=None):
     path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
     data = np.load(path, allow_pickle=False)

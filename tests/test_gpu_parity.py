@@ -115,6 +115,75 @@ def test_golden_alie(api, golden, nm):
             assert all(u.grads is users[0].grads for u in users) and users[0].grads is att.grads_mean
 
 
+def _fake_training(p):                                   # same stand-in for backdoor.py:108 as make_golden_backdoor.py
+    if isinstance(p, torch.Tensor):
+        return p * 0.9 + 0.01
+    return (p * np.float32(0.9) + np.float32(0.01)).astype(np.float32)
+
+
+@pytest.mark.parametrize("nm", ["d8", "d1000", "d4099_tight", "d257_wide"])
+def test_golden_backdoor_hook(api, golden_backdoor, nm):
+    """BackdoorAttack._attack_grads (backdoor.py:52-65): elementwise fp32 arithmetic -> bit-exact."""
+    _, M, *_ = api
+    g = golden_backdoor
+    z, lr = float(g[f"hook_{nm}/z"]), float(g[f"hook_{nm}/lr"])
+    for to_dev in (False, True):
+        conv = (lambda a: torch.from_numpy(a.copy()).cuda()) if to_dev else (lambda a: a.copy())
+        got = M.BackdoorAttack(z, _fake_training)._attack_grads(conv(g[f"hook_{nm}/mean"]), conv(g[f"hook_{nm}/stdev"]),
+                                                               conv(g[f"hook_{nm}/params"]), lr)
+        got = got.cpu().numpy() if to_dev else got
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), g[f"hook_{nm}/want"].view(np.uint32))
+
+
+@pytest.mark.parametrize("nm", ["f5_d300", "f24_d2051"])
+def test_golden_backdoor_attack(api, golden_backdoor, nm):
+    """Attack.attack (malicious.py:10-27) driving the backdoor hook: statistics, hook, aliasing."""
+    _, M, *_ = api
+    g = golden_backdoor
+    z, lr = float(g[f"attack_{nm}/z"]), float(g[f"attack_{nm}/lr"])
+
+    class U:
+        def __init__(self, gr, w): self.grads = gr; self.original_params = w; self.learning_rate = lr
+    for to_dev in (False, True):
+        conv = (lambda a: torch.from_numpy(a.copy()).cuda()) if to_dev else (lambda a: a.copy())
+        w = conv(g[f"attack_{nm}/params"])
+        users = [U(conv(r), w) for r in g[f"attack_{nm}/rows"]]
+        att = M.BackdoorAttack(z, _fake_training); att.attack(users)
+        back = (lambda a: a.cpu().numpy()) if to_dev else (lambda a: a)
+        np.testing.assert_allclose(back(att.grads_stdev), g[f"attack_{nm}/stdev"], rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(back(att.grads_mean), g[f"attack_{nm}/mean"], rtol=RTOL, atol=1e-6)
+        # the band moves with mu/sigma (fp32 rounding of the one-pass moments), so compare with the oracle
+        # evaluated on the device's own statistics: that must be bit-exact
+        want = orc.backdoor_attack_grads(back(att.grads_mean).copy(), back(att.grads_stdev).copy(), g[f"attack_{nm}/params"],
+                                         lr, z, _fake_training)
+        got = back(users[0].grads)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        np.testing.assert_allclose(got, g[f"attack_{nm}/grads0"], rtol=1e-5, atol=2e-5)
+        assert all(u.grads is users[0].grads for u in users)
+
+
+def test_alie_band_semantics(api):
+    _, M, dev, _ = api
+    rng = np.random.default_rng(3)
+    d = 100003
+    mu = rng.standard_normal(d).astype(np.float32); sd = np.abs(rng.standard_normal(d)).astype(np.float32)
+    x = (3 * rng.standard_normal(d)).astype(np.float32)
+    x[5] = np.nan; x[6] = np.inf; x[7] = -np.inf; sd[9] = np.nan; sd[11] = 0.0
+    for z in (0.0, 0.25, 1.5):
+        want = np.clip(x, mu - z * sd, mu + z * sd)
+        got = M.backdoor_clip(x, mu, sd, z)
+        assert np.array_equal(got.view(np.uint32) & 0x7fffffff >= 0x7f800001, np.isnan(want))      # NaNs in the same places
+        ok = ~np.isnan(want)
+        assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32))
+        m2 = mu.copy(); m2[:] -= z * sd                                                          # malicious.py:35
+        got2 = M.DriftAttack(z)._attack_grads(mu.copy(), sd.copy(), None, None)
+        ok2 = ~np.isnan(m2)
+        assert np.array_equal(got2[ok2].view(np.uint32), m2[ok2].view(np.uint32))
+    mud, sdd = torch.from_numpy(mu).cuda(), torch.from_numpy(sd).cuda()
+    ret = M.DriftAttack(1.5)._attack_grads(mud, sdd, None, None)
+    assert ret is mud                                                                            # in place, same object
+
+
 # ------------------------------------------------------------------ seeded random inputs vs the oracle
 @pytest.mark.parametrize("n,d,f,seed", [(10, 79510, 2, 0), (100, 40000, 24, 1), (37, 12345, 8, 2), (130, 8192, 30, 3),
                                         (300, 4096, 70, 4)])

@@ -45,11 +45,28 @@ def test_distance_table_mapping_protocol():
         t.pop(0)
 
 
-def test_drift_attack_hook_matches_reference_arithmetic():
-    a = M.DriftAttack(1.5)
+def test_attack_hooks_have_no_cpu_fallback():
+    """The hooks compute on the device even for NumPy arguments: without a GPU they must fail loudly,
+    not fall back to host arithmetic (the arithmetic itself is checked by the -m gpu tests)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; covered by tests/test_gpu_parity.py::test_alie_band_semantics")
     mu = np.array([1.0, 2.0], np.float32); sd = np.array([0.5, 0.25], np.float32)
-    out = a._attack_grads(mu, sd, None, None)
-    assert out is mu and np.array_equal(mu, np.array([0.25, 1.625], np.float32))
+    with pytest.raises(Exception):
+        M.DriftAttack(1.5)._attack_grads(mu, sd, None, None)
+    with pytest.raises(Exception):
+        M.BackdoorAttack(1.5, lambda p: p)._attack_grads(mu, sd, mu.copy(), 0.1)
+    with pytest.raises(Exception):
+        M.backdoor_clip(mu, mu, sd, 1.0)
+    assert np.array_equal(mu, np.array([1.0, 2.0], np.float32))          # untouched
+
+
+def test_attack_success_metrics():
+    from attacking_federate_learning_b200 import metrics
+    assert metrics.krum_attack_success(0, 24) and metrics.krum_attack_success(23, 24)
+    assert not metrics.krum_attack_success(24, 24) and not metrics.krum_attack_success(-1, 24)
+    assert metrics.bulyan_attack_success([0, 1, 50, 51], 2) == 0.5
+    assert metrics.bulyan_attack_success([], 2) == 0.0
 
 
 @pytest.mark.parametrize("dim,world", [(25_000_000, 8), (11_200_000, 4), (79_510, 2), (100, 8), (31, 2)])
