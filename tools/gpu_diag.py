@@ -287,6 +287,8 @@ reg("b16_n97", case_gram, 97, 40_000, F["TC"] | 32, "b16_n97")
 for sp in ["37","74"]:
     reg(f"b16_sp{sp}", case_gram, 100, 11_200_000, F["TC"], f"b16_sp{sp}", True, env={"AFL_GRAM_SPLITS": sp})
 reg("b16_flush2", case_gram, 100, 11_200_000, F["TC"], "b16_flush2", True, env={"AFL_GRAM_FLUSH": "2"})
+reg("b16_flush8", case_gram, 100, 11_200_000, F["TC"], "b16_flush8", True, env={"AFL_GRAM_FLUSH": "8"})
+reg("b16_flush16", case_gram, 100, 11_200_000, F["TC"], "b16_flush16", True, env={"AFL_GRAM_FLUSH": "16"})
 for pf in ["0","1","2","4"]:
     reg(f"b16_pf{pf}", case_gram, 100, 11_200_000, F["TC"], f"b16_pf{pf}", True, env={"AFL_GRAM_PREFETCH": pf})
 for kn in ["1","2","4","3","6"]:
