@@ -329,7 +329,7 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
     attr_set = true;
   }
   {
-    ProfScope ps("gram_tcgen05", stream);
+    ProfScope ps("gram_bf16x2", stream);
     gram_bf16x2_kernel<<<splits, kB16Threads, smem, stream>>>(tmap, p);
   }
   AFL_LAUNCH_CHECK("gram_bf16x2_kernel");

@@ -70,7 +70,7 @@ uint64_t afl_launch_count(void);
 /* ---- in-library kernel timing (measurement aid for bench.py) -----------------------------------
  * While enabled, the dominant kernel of every entry point is bracketed by CUDA events on the stream it
  * is launched on.  afl_profile_read(name, ...) waits for the recorded events of kernel `name`
- * ("gram_tcgen05", "sqdist_simt", "trimmed_mean", "alie", "mean", "row_sort", "bulyan_rounds"),
+ * ("gram_bf16x2", "gram_tcgen05", "sqdist_simt", "trimmed_mean", "alie", "mean", "row_sort", "bulyan_rounds"),
  * returns their summed duration and launch count, and forgets them. */
 int afl_profile_enable(int on);
 int afl_profile_read(const char* kernel, double* total_ms, int* launches);
