@@ -1,0 +1,35 @@
+"""bench.py's reference arm (`--impl reference`) runs the CPU port of the reference algorithm and needs no
+GPU: check that it prints ONE JSON line with the contract's keys (tiny configuration, ~1 s of CPU work)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_reference_arm(*extra):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-budget", "1", *extra], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_the_contract_line():
+    line = run_reference_arm("--n", "20", "--d", "20000")
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "aggregations/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "N=20" in line["metric"] and "N=20" in line["config"]["workload"]
+
+
+def test_reference_arm_other_rules():
+    for rule in ("TrimmedMean", "Bulyan", "NoDefense"):
+        line = run_reference_arm("--rule", rule, "--n", "23", "--d", "4000", "--f", "5")
+        assert rule in line["metric"] and line["value"] > 0
