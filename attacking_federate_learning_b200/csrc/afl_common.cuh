@@ -32,7 +32,19 @@ void count_launch(int n = 1);
     if (_e != cudaSuccess) return ::afl::cuda_fail(_e, name, __FILE__, __LINE__); \
   } while (0)
 
-int sm_count();
+constexpr int kMaxDevices = 64;
+int current_device();      // ordinal of the current device (0 when no device is visible)
+int sm_count();            // SM count of the CURRENT device
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device).
+template <typename K>
+static inline cudaError_t ensure_dyn_smem(K kernel, int bytes, int (&done)[kMaxDevices]) {
+  const int dev = current_device();
+  if (done[dev] >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = bytes;
+  return e;
+}
 
 // Optional CUDA-event bracket around a kernel launch (active only after afl_profile_enable(1)).
 struct ProfScope {

@@ -66,17 +66,24 @@ static int profile_read(const char* kernel, double* total_ms, int* launches) {
   return AFL_OK;
 }
 
+// Per-device state: the C ABI promises "current device" semantics (afl_b200.h), so nothing below may
+// remember the first device it saw.
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
 int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-      cached = sms;
+  static int cached[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!cached[dev]) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      cached[dev] = sms;
     else
       return 148;   // B200; used only for workspace sizing when no device is visible
   }
-  return cached;
+  return cached[dev];
 }
 
 namespace gram {
@@ -123,7 +130,7 @@ struct HostCtx {
   cudaEvent_t ev[64];
   bool init = false;
 };
-static HostCtx g_ctx;
+static HostCtx g_ctx[kMaxDevices];
 
 static int ensure(void** p, size_t* have, size_t want) {
   if (*have >= want) return AFL_OK;
@@ -152,7 +159,7 @@ static int defend_host(const char* rule, const float* G, int n, int64_t d, int64
     set_error("bulyan: users_count >= 4*corrupted_count + 3 violated (%d, %d)", users_count, f);
     return AFL_ERR_PRECONDITION;
   }
-  HostCtx& c = g_ctx;
+  HostCtx& c = g_ctx[current_device()];          // streams, events and buffers belong to the current device
   std::lock_guard<std::mutex> lock(c.mu);
   if (!c.init) {
     AFL_CUDA(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
@@ -164,7 +171,7 @@ static int defend_host(const char* rule, const float* G, int n, int64_t d, int64
   const size_t mat_bytes = static_cast<size_t>(n) * ld_dev * sizeof(float);
   size_t free_b = 0, total_b = 0;
   AFL_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  if (mat_bytes > c.mat_bytes && mat_bytes > free_b + c.mat_bytes - (size_t(1) << 30)) {
+  if (mat_bytes > c.mat_bytes && mat_bytes + (size_t(1) << 30) > free_b + c.mat_bytes) {   // keep 1 GiB of headroom
     set_error("afl_defend_host: %zu-byte matrix does not fit on this GPU; shard the parameter dimension", mat_bytes);
     return AFL_ERR_UNSUPPORTED;
   }
@@ -234,6 +241,13 @@ static int defend_host(const char* rule, const float* G, int n, int64_t d, int64
     rc = select::bulyan_select(dist, n, users_count, f, sel, sel_ws, c.ws_bytes - gram_ws_bytes, c.comp); if (rc) return rc;
     const int theta = users_count - 2 * f;
     rc = tmean::trimmed_mean(mat, n, d, ld_dev, AFL_F32, sel, theta, 2 * f, out_dev, c.comp); if (rc) return rc;
+    int last_sel = 0;                                  // a failed round marks itself and every later round with -1
+    AFL_CUDA(cudaMemcpyAsync(&last_sel, sel + (theta - 1), sizeof(int), cudaMemcpyDeviceToHost, c.comp));
+    AFL_CUDA(cudaStreamSynchronize(c.comp));
+    if (last_sel < 0) {
+      set_error("bulyan: a selection round found no eligible user (NaN or >= 1e20 scores); the reference raises KeyError(-1)");
+      return AFL_ERR_NO_WINNER;
+    }
   }
   AFL_CUDA(cudaMemcpyAsync(out_host, out_dev, static_cast<size_t>(d) * sizeof(float), cudaMemcpyDeviceToHost, c.comp));
   AFL_CUDA(cudaStreamSynchronize(c.comp));

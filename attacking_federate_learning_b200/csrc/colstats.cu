@@ -35,6 +35,41 @@ template <> __device__ __forceinline__ Pack<1> load_pack<__nv_bfloat16, 1>(const
   return Pack<1>{{__bfloat162float(*p)}};
 }
 
+// Coherent variants (no .nc, no L1 bypass hint): used when the kernel also WRITES the matrix it reads
+// (ALIE writing the crafted vector back into the malicious rows it just reduced).
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<VEC> load_pack_coherent(const T* p) {
+  Pack<VEC> r;
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (VEC == 4) {
+      float4 t;
+      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p) : "memory");
+      r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+      float t;
+      asm volatile("ld.global.f32 %0, [%1];" : "=f"(t) : "l"(p) : "memory");
+      r.v[0] = t;
+    }
+  } else {
+    if constexpr (VEC == 8) {
+      uint32_t w[4];
+      asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p) : "memory");
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { r.v[2 * i] = bf16_bits_to_f32(w[i] & 0xFFFFu); r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    } else {
+      uint16_t t;
+      asm volatile("ld.global.u16 %0, [%1];" : "=h"(t) : "l"(p) : "memory");
+      r.v[0] = bf16_bits_to_f32(t);
+    }
+  }
+  return r;
+}
+template <typename T, int VEC, bool COHERENT>
+__device__ __forceinline__ Pack<VEC> load_rows(const T* p) {
+  if constexpr (COHERENT) return load_pack_coherent<T, VEC>(p);
+  else return load_pack<T, VEC>(p);
+}
+
 // ---- mean: sequential fp32 row accumulation, then one IEEE division — the order NumPy uses for
 // np.mean(axis=0) on a C-contiguous array, so fp32 results are bit-identical to the reference.
 template <typename T, int VEC>
@@ -70,15 +105,14 @@ mean_kernel(const T* __restrict__ G, int n, int64_t d, int64_t ld, float* __rest
 // ---- ALIE: one pass, shifted moments (shift = the first malicious row, so |x - shift| ~ sigma and
 // E[dx^2] - E[dx]^2 does not cancel).  sigma = sqrt(population variance); crafted = mu - z*sigma with
 // the same two roundings as `grads_mean[:] -= num_std * grads_stdev[:]` in fp32.
-template <typename T, int VEC>
+template <typename T, int VEC, bool COHERENT>
 __global__ void __launch_bounds__(kBlock)
-alie_kernel(const T* __restrict__ G, int f, int64_t d, int64_t ld, float z, float* __restrict__ mu_out,
-            float* __restrict__ sigma_out, float* __restrict__ crafted_out, float* __restrict__ bcast,
-            int64_t bcast_ld) {
+alie_kernel(const T* G, int f, int64_t d, int64_t ld, float z, float* __restrict__ mu_out,
+            float* __restrict__ sigma_out, float* __restrict__ crafted_out, float* bcast, int64_t bcast_ld) {
   const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * VEC;
   if (c0 >= d) return;
   const T* p = G + c0;
-  const Pack<VEC> shift = load_pack<T, VEC>(p);
+  const Pack<VEC> shift = load_rows<T, VEC, COHERENT>(p);
   float s1[VEC], s2[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
@@ -86,7 +120,7 @@ alie_kernel(const T* __restrict__ G, int f, int64_t d, int64_t ld, float z, floa
   for (; r + kUnroll <= f; r += kUnroll) {
     Pack<VEC> t[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) t[u] = load_pack<T, VEC>(p + static_cast<int64_t>(r + u) * ld);
+    for (int u = 0; u < kUnroll; ++u) t[u] = load_rows<T, VEC, COHERENT>(p + static_cast<int64_t>(r + u) * ld);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
@@ -97,7 +131,7 @@ alie_kernel(const T* __restrict__ G, int f, int64_t d, int64_t ld, float z, floa
       }
   }
   for (; r < f; ++r) {
-    Pack<VEC> t = load_pack<T, VEC>(p + static_cast<int64_t>(r) * ld);
+    Pack<VEC> t = load_rows<T, VEC, COHERENT>(p + static_cast<int64_t>(r) * ld);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float dx = t.v[k] - shift.v[k];
@@ -106,20 +140,36 @@ alie_kernel(const T* __restrict__ G, int f, int64_t d, int64_t ld, float z, floa
     }
   }
   const float inv = 1.0f / static_cast<float>(f);
+  float crafted[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    if (c0 + k >= d) break;
     const float m1 = s1[k] * inv;
     const float mu = shift.v[k] + m1;
     float var = fmaf(-m1, m1, s2[k] * inv);
     var = var > 0.f ? var : 0.f;
     const float sigma = sqrtf(var);
-    const float crafted = __fsub_rn(mu, __fmul_rn(z, sigma));
-    if (sigma_out) sigma_out[c0 + k] = sigma;
-    if (mu_out && mu_out != crafted_out) mu_out[c0 + k] = mu;
-    if (crafted_out) crafted_out[c0 + k] = crafted;
-    if (bcast)
-      for (int rr = 0; rr < f; ++rr) bcast[static_cast<int64_t>(rr) * bcast_ld + c0 + k] = crafted;
+    crafted[k] = __fsub_rn(mu, __fmul_rn(z, sigma));
+    if (c0 + k < d) {
+      if (sigma_out) sigma_out[c0 + k] = sigma;
+      if (mu_out && mu_out != crafted_out) mu_out[c0 + k] = mu;
+      if (crafted_out) crafted_out[c0 + k] = crafted[k];
+    }
+  }
+  if (bcast) {
+    // server.py:82-83 copies the one aliased array into every malicious row: f row segments of VEC floats,
+    // written as 16-byte stores when the destination allows it (all of this thread's reads are done)
+    const bool v16 = (VEC % 4 == 0) && (c0 + VEC <= d) && (bcast_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(bcast) & 15) == 0);
+    for (int rr = 0; rr < f; ++rr) {
+      float* dst = bcast + static_cast<int64_t>(rr) * bcast_ld + c0;
+      if (v16) {
+#pragma unroll
+        for (int k = 0; k + 4 <= VEC; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(crafted[k], crafted[k + 1], crafted[k + 2], crafted[k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if (c0 + k < d) dst[k] = crafted[k];
+      }
+    }
   }
 }
 
@@ -199,13 +249,20 @@ int alie(const void* G, int f, int64_t d, int64_t ld, int dtype, double z, float
   const unsigned grid = static_cast<unsigned>(ceil_div64(ceil_div64(d, vec), kBlock));
   const float zf = static_cast<float>(z);
   ProfScope ps("alie", stream);
+  // the reference writes the crafted vector back over the malicious rows (main.py:68 -> server.py:82-83): when the
+  // broadcast target overlaps the input, read it coherently (no ld.global.nc on memory this launch writes)
+  const uintptr_t g0 = reinterpret_cast<uintptr_t>(G), g1 = g0 + static_cast<uintptr_t>((static_cast<int64_t>(f - 1) * ld + d) * (dtype == AFL_F32 ? 4 : 2));
+  const uintptr_t b0 = reinterpret_cast<uintptr_t>(bcast), b1 = b0 + static_cast<uintptr_t>((static_cast<int64_t>(f - 1) * bcast_ld + d) * 4);
+  const bool coh = bcast && b0 < g1 && g0 < b1;
+#define AFL_ALIE_LAUNCH(T, V, C) alie_kernel<T, V, C><<<grid, kBlock, 0, stream>>>(static_cast<const T*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld)
   if (dtype == AFL_F32) {
-    if (v) alie_kernel<float, 4><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
-    else alie_kernel<float, 1><<<grid, kBlock, 0, stream>>>(static_cast<const float*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
+    if (v) { if (coh) AFL_ALIE_LAUNCH(float, 4, true); else AFL_ALIE_LAUNCH(float, 4, false); }
+    else { if (coh) AFL_ALIE_LAUNCH(float, 1, true); else AFL_ALIE_LAUNCH(float, 1, false); }
   } else {
-    if (v) alie_kernel<__nv_bfloat16, 8><<<grid, kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
-    else alie_kernel<__nv_bfloat16, 1><<<grid, kBlock, 0, stream>>>(static_cast<const __nv_bfloat16*>(G), f, d, ld, zf, mu_out, sigma_out, crafted_out, bcast, bcast_ld);
+    if (v) { if (coh) AFL_ALIE_LAUNCH(__nv_bfloat16, 8, true); else AFL_ALIE_LAUNCH(__nv_bfloat16, 8, false); }
+    else { if (coh) AFL_ALIE_LAUNCH(__nv_bfloat16, 1, true); else AFL_ALIE_LAUNCH(__nv_bfloat16, 1, false); }
   }
+#undef AFL_ALIE_LAUNCH
   AFL_LAUNCH_CHECK("alie_kernel");
   return AFL_OK;
 }

@@ -633,11 +633,8 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
     const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 +
                         ((pl.tiles == 1 && pl.stage_bytes < kTileBytes) ? (kTileBytes - pl.stage_bytes) : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-      AFL_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      attr_set = true;
-    }
+  static int smem_attr_done[kMaxDevices] = {0};
+  AFL_CUDA(ensure_dyn_smem(gram_tcgen05_kernel, 226 * 1024, smem_attr_done));
     const char* trace_path = getenv("AFL_GRAM_TRACE");      // debug aid: dump per-role clock64 timestamps
     if (trace_path && *trace_path) {
       AFL_CUDA(cudaMalloc(&p.trace, sizeof(long long) * 2 * kTraceLen * kTraceEv));

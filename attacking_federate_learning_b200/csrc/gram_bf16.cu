@@ -323,11 +323,8 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", static_cast<int>(r)); return AFL_ERR_CUDA; }
   const size_t smem = static_cast<size_t>(kRawSlots) * n * 256 + static_cast<size_t>(kBfStages) * p.nb * 256 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AFL_CUDA(cudaFuncSetAttribute(gram_bf16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
-  }
+  static int smem_attr_done[kMaxDevices] = {0};
+  AFL_CUDA(ensure_dyn_smem(gram_bf16x2_kernel, 226 * 1024, smem_attr_done));
   {
     ProfScope ps("gram_bf16x2", stream);
     gram_bf16x2_kernel<<<splits, kB16Threads, smem, stream>>>(tmap, p);

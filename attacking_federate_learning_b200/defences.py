@@ -201,6 +201,8 @@ def bulyan(users_grads, users_count, corrupted_count, return_selection=False):
         dist = dev.sqdist_to_dist(dev.sqdist_partial(users_grads))
         sel = dev.bulyan_select(dist, users_count, corrupted_count)
         out = dev.trimmed_mean(users_grads, 2 * corrupted_count, row_index=sel)
+        if sel.numel() and int(sel[-1].item()) < 0:      # a failed round marks itself and all later rounds with -1
+            raise KeyError(-1)                           # defences.py:66 `distances.pop(-1)`
         return (out, sel) if return_selection else out
     out, _ = _host_call(DefenseTypes.Bulyan, _as_host_matrix(users_grads), users_count, corrupted_count)
     return out

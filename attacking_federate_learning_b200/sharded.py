@@ -68,6 +68,8 @@ class ShardedAggregator:
         assert users_count >= 4 * corrupted_count + 3
         sel = self.k.bulyan_select(self.distances(G_shard), users_count, corrupted_count)
         out = self.k.trimmed_mean(G_shard, 2 * corrupted_count, row_index=sel)
+        if len(sel) and int(sel[-1]) < 0:                # no eligible user in some round: defences.py:66 raises KeyError(-1)
+            raise KeyError(-1)
         return (out, sel) if return_selection else out
 
     def trimmed_mean(self, G_shard, users_count, corrupted_count):
@@ -76,9 +78,17 @@ class ShardedAggregator:
     def no_defense(self, G_shard, users_count=None, corrupted_count=None):
         return self.k.mean(G_shard)
 
-    def alie(self, G_shard, corrupted_count, num_std):
-        crafted, _, _ = self.k.alie(G_shard[:corrupted_count], num_std, G_shard if G_shard.dtype == torch.float32 else None)
+    def alie(self, G_shard, corrupted_count, num_std, write_rows=True, source_rows=None):
+        """malicious.py:10-27 on this column shard: statistics over the malicious rows (rows 0..f-1, or
+        `source_rows` = a [f, d_local] view of their honest gradients), crafted = mu - z*sigma, written back into
+        rows 0..f-1 of the matrix when `write_rows` (what server.py:82-83 does with the aliased arrays)."""
+        src = G_shard[:corrupted_count] if source_rows is None else source_rows
+        bcast = G_shard if (write_rows and G_shard.dtype == torch.float32) else None
+        crafted, _, _ = self.k.alie(src, num_std, bcast)
         return crafted
+
+    def exchange_name(self):
+        return "NCCL all-reduce" if self.world > 1 else "none"
 
     def defend(self, name, G_shard, users_count, corrupted_count):
         return {"Krum": self.krum, "TrimmedMean": self.trimmed_mean, "NoDefense": self.no_defense,

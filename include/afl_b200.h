@@ -42,7 +42,9 @@ typedef enum afl_status {
   AFL_ERR_PRECONDITION = 2,  /* the reference's `assert` would fire (n >= 2f+1, n >= 4f+3)         */
   AFL_ERR_CUDA = 3,          /* a CUDA call failed; see afl_last_error()                          */
   AFL_ERR_UNSUPPORTED = 4,   /* dtype / size outside what the kernels implement                   */
-  AFL_ERR_WORKSPACE = 5      /* workspace too small                                               */
+  AFL_ERR_WORKSPACE = 5,     /* workspace too small                                               */
+  AFL_ERR_NO_WINNER = 6      /* a Bulyan round found no eligible user (NaN / >= 1e20 scores): the      */
+                             /* reference raises KeyError(-1) at defences.py:66 (`distances.pop(-1)`)  */
 } afl_status;
 
 typedef enum afl_dtype { AFL_F32 = 0, AFL_BF16 = 1 } afl_dtype;

@@ -23,6 +23,10 @@ def lib():
         L.orc_krum_select.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_bulyan_select.restype = C.c_int
         L.orc_bulyan_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_bulyan_select_m.restype = C.c_int
+        L.orc_bulyan_select_m.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_krum_select_m.restype = C.c_int
+        L.orc_krum_select_m.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_trimmed_mean.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_mean.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_alie.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -52,16 +56,21 @@ def pairwise_dist_as_f32(G):
     return np.sqrt(pairwise_sqdist(G)).astype(np.float32)
 
 
-def krum_select(dist, users_count, corrupted_count):
+def krum_select(dist, users_count, corrupted_count, with_margin=False):
     t = np.ascontiguousarray(dist, np.float64)
-    return lib().orc_krum_select(t.ctypes.data, t.shape[0], None, users_count, corrupted_count, None)
+    if not with_margin:
+        return lib().orc_krum_select(t.ctypes.data, t.shape[0], None, users_count, corrupted_count, None)
+    m = C.c_double(0.0)
+    idx = lib().orc_krum_select_m(t.ctypes.data, t.shape[0], None, users_count, corrupted_count, C.addressof(m))
+    return idx, m.value
 
 
-def bulyan_select(dist, n, f):
+def bulyan_select(dist, n, f, with_margins=False):
     t = np.ascontiguousarray(dist, np.float64)
     sel = np.empty(max(n - 2 * f, 1), np.int32)
-    got = lib().orc_bulyan_select(t.ctypes.data, n, f, sel.ctypes.data)
-    return sel[:got].tolist()
+    mg = np.empty(max(n - 2 * f, 1), np.float64)
+    got = lib().orc_bulyan_select_m(t.ctypes.data, n, f, sel.ctypes.data, mg.ctypes.data)
+    return (sel[:got].tolist(), mg[:got].tolist()) if with_margins else sel[:got].tolist()
 
 
 def trimmed_mean(G, corrupted_count, rows=None):

@@ -150,19 +150,50 @@ int orc_krum_select(const double* dist, int n, const unsigned char* alive, int u
   return best_idx;
 }
 
-/* defences.py:57-68 — theta = n - 2f rounds of Krum with removal on one table. */
-int orc_bulyan_select(const double* dist, int n, int f, int* sel_out) {
+/* Relative gap between the winning score and the runner-up of one scan (0 = exact tie, resolved by
+ * visit order; inf when there is no runner-up).  Used by the tests to tell a selection the CUDA path
+ * must reproduce from one inside fp32 noise. */
+static double scan_margin(const double* score, int n, const unsigned char* alive, int best_idx) {
+  if (best_idx < 0) return INFINITY;
+  double second = INFINITY;
+  for (int u = 0; u < n; ++u) {
+    if (u == best_idx || (alive && !alive[u])) continue;
+    if (score[u] < second) second = score[u];
+  }
+  const double best = score[best_idx];
+  if (!(second < INFINITY) || best == 0.0) return INFINITY;
+  return (second - best) / fabs(best);
+}
+
+/* orc_krum_select + margin */
+int orc_krum_select_m(const double* dist, int n, const unsigned char* alive, int users_count, int corrupted_count,
+                      double* margin_out) {
+  double* score = (double*)malloc(sizeof(double) * (size_t)n);
+  const int idx = orc_krum_select(dist, n, alive, users_count, corrupted_count, score);
+  if (margin_out) *margin_out = scan_margin(score, n, alive, idx);
+  free(score);
+  return idx;
+}
+
+/* defences.py:57-68 — theta = n - 2f rounds of Krum with removal on one table.
+ * margins_out (may be NULL): per-round relative gap to the runner-up. */
+int orc_bulyan_select_m(const double* dist, int n, int f, int* sel_out, double* margins_out) {
   const int theta = n - 2 * f;
   unsigned char* alive = (unsigned char*)malloc((size_t)n);
+  double* score = (double*)malloc(sizeof(double) * (size_t)n);
   memset(alive, 1, (size_t)n);
   for (int r = 0; r < theta; ++r) {
-    const int idx = orc_krum_select(dist, n, alive, n - r, f, NULL);
+    const int idx = orc_krum_select(dist, n, alive, n - r, f, score);
     sel_out[r] = idx;
-    if (idx < 0) { free(alive); return r; }
+    if (margins_out) margins_out[r] = scan_margin(score, n, alive, idx);
+    if (idx < 0) { free(alive); free(score); return r; }
     alive[idx] = 0;
   }
-  free(alive);
+  free(alive); free(score);
   return theta;
+}
+int orc_bulyan_select(const double* dist, int n, int f, int* sel_out) {
+  return orc_bulyan_select_m(dist, n, f, sel_out, NULL);
 }
 
 typedef struct { float key; float dev; int row; } kd_t;
