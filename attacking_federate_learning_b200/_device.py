@@ -164,3 +164,60 @@ def momentum_step(weights: torch.Tensor, velocity: torch.Tensor, grads: torch.Te
     with torch.cuda.device(weights.device):
         nat.check(nat.lib().afl_momentum_step(weights.data_ptr(), velocity.data_ptr(), grads.data_ptr(), d,
                                               float(momentum), float(lr), _stream_ptr(weights)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU exchange over NVLink peer memory (csrc/xgpu.cu)
+# ---------------------------------------------------------------------------------------------------------
+import ctypes as _C
+
+
+class PeerContext:
+    """One rank's side of the peer-memory exchange: owns the native context and the mapped result words."""
+
+    def __init__(self, world: int, rank: int, n_max: int, device):
+        self.world, self.rank, self.n_max, self.device = world, rank, n_max, device
+        self.ctx = _C.c_void_p()
+        with torch.cuda.device(device):
+            nat.check(nat.lib().afl_xgpu_create(world, rank, n_max, _C.byref(self.ctx)))
+        self._idx = _C.POINTER(_C.c_int)()
+        self._status = _C.POINTER(_C.c_int)()
+        self._idx_dev = _C.POINTER(_C.c_int)()
+
+    def handle(self) -> bytes:
+        buf = _C.create_string_buffer(64)
+        nat.check(nat.lib().afl_xgpu_handle(self.ctx, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().afl_xgpu_connect(self.ctx, b"".join(handles)))
+
+    def close(self):
+        if self.ctx:
+            nat.lib().afl_xgpu_destroy(self.ctx)
+            self.ctx = _C.c_void_p()
+
+    def krum(self, G: torch.Tensor, users_count: int, corrupted_count: int, flags: int = 0) -> int:
+        """Enqueue gram -> publish -> fused tail, synchronise the stream once, return the index."""
+        n, d, ld = check_matrix(G)
+        L = nat.lib()
+        with torch.cuda.device(G.device):
+            ws = Workspace.get(G.device, "gram", L.afl_sqdist_workspace_bytes(n, d, dtype_code(G), flags))
+            nat.check(L.afl_krum_sharded(self.ctx, G.data_ptr(), n, d, ld, dtype_code(G), users_count, corrupted_count,
+                                         ws.data_ptr(), ws.numel(), flags, _stream_ptr(G), _C.byref(self._idx),
+                                         _C.byref(self._status), _C.byref(self._idx_dev)))
+            torch.cuda.current_stream(G.device).synchronize()
+        if self._status[0] != 0:
+            raise RuntimeError("afl_krum_sharded: a peer rank did not publish its partial table in time")
+        return int(self._idx[0])
+
+    def allreduce_table(self, G: torch.Tensor, out: torch.Tensor, flags: int = 0) -> torch.Tensor:
+        """Partial table of this shard summed over all ranks into `out` ([n, n] float64); enqueues only."""
+        n, d, ld = check_matrix(G)
+        L = nat.lib()
+        with torch.cuda.device(G.device):
+            ws = Workspace.get(G.device, "gram", L.afl_sqdist_workspace_bytes(n, d, dtype_code(G), flags))
+            nat.check(L.afl_sqdist_allreduce(self.ctx, G.data_ptr(), n, d, ld, dtype_code(G), out.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), flags, _stream_ptr(G), _C.byref(self._status)))
+        return out

@@ -15,6 +15,7 @@ AFL_F32, AFL_BF16 = 0, 1
 GRAM_AUTO, GRAM_FORCE_SIMT, GRAM_FORCE_TCGEN05, GRAM_SINGLE_PASS, GRAM_REWRITE_HI = 0, 1, 2, 4, 8
 GRAM_TF32X2 = 16
 GRAM_BF16X2 = 32
+GRAM_NO_CENTER = 64
 
 _vp, _i, _i64, _sz, _d, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double, C.c_float
 
@@ -35,10 +36,18 @@ SIGNATURES = {
     "afl_krum_from_sqdist": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "afl_bulyan_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "afl_trimmed_mean": (_i, [_vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp]),
+    "afl_debug_tm_stats": (_i, [C.POINTER(C.c_uint64), _i]),
     "afl_gather_row": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),
     "afl_alie": (_i, [_vp, _i, _i64, _i64, _i, _d, _vp, _vp, _vp, _vp, _i64, _vp]),
     "afl_alie_band": (_i, [_vp, _vp, _d, _vp, _vp, _i64, _vp]),
     "afl_momentum_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _vp]),
+    "afl_xgpu_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
+    "afl_xgpu_handle": (_i, [_vp, C.c_char_p]),
+    "afl_xgpu_connect": (_i, [_vp, C.c_char_p]),
+    "afl_xgpu_destroy": (_i, [_vp]),
+    "afl_krum_sharded": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _sz, _i, _vp, C.POINTER(C.POINTER(_i)),
+                              C.POINTER(C.POINTER(_i)), C.POINTER(C.POINTER(_i))]),
+    "afl_sqdist_allreduce": (_i, [_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _sz, _i, _vp, C.POINTER(C.POINTER(_i))]),
     "afl_defend_host": (_i, [C.c_char_p, _vp, _i, _i64, _i64, _i, _i, _vp, C.POINTER(_i), _i64]),
 }
 
@@ -97,3 +106,10 @@ def profile_read(kernel: str):
     ms, cnt = _d(0.0), _i(0)
     check(lib().afl_profile_read(kernel.encode(), C.byref(ms), C.byref(cnt)))
     return ms.value, cnt.value
+
+
+def tm_stats(reset: bool = False):
+    """(columns sent to the general path, bracket retries) of the packed bf16 trimmed-mean kernel since the last reset."""
+    out = (C.c_uint64 * 4)()
+    check(lib().afl_debug_tm_stats(out, 1 if reset else 0))
+    return int(out[1]), int(out[2])

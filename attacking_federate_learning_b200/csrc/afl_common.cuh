@@ -10,6 +10,10 @@
 
 #include "../../include/afl_b200.h"
 
+#ifndef AFL_BAR_TIMEOUT_LOG2
+#define AFL_BAR_TIMEOUT_LOG2 32
+#endif
+
 namespace afl {
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +131,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 32)) {                  // ~2 s: no legitimate wait is longer than one pipeline step
+    if (clock64() - t0 > (1ll << AFL_BAR_TIMEOUT_LOG2)) {  // ~2 s by default: no legitimate wait is longer than one pipeline step
       printf("afl: mbarrier timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
              smem_u32(bar), parity);
       __trap();
@@ -273,6 +277,34 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t m, uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+
+// Centre of the bf16x2 Gram kernels: mean of the LAST `rows` clients (cref = first of those rows, pitch ld) over
+// this lane's 4 consecutive columns starting at `col`.  Distances are translation invariant, so any centre is
+// correct; a centre close to the clients' common component keeps ||g - c||^2 (which the dropped-term and
+// accumulation biases scale with) of the order of the distances themselves.  Ids >= f are honest (main.py:28).
+constexpr int kGramCenterRows = 8;
+__device__ __forceinline__ float4 gram_center(const float* cref, int rows, int64_t ld, int64_t col, int64_t d) {
+  // always kGramCenterRows loads, all issued before the first add (a runtime trip count would serialise 8 dependent
+  // L2 round trips per k-block); with fewer clients the last row is simply counted more than once - any centre is valid
+  float4 t[kGramCenterRows];
+  if (col + 3 < d) {
+#pragma unroll
+    for (int r = 0; r < kGramCenterRows; ++r)
+      t[r] = __ldg(reinterpret_cast<const float4*>(cref + static_cast<int64_t>(r < rows ? r : rows - 1) * ld + col));
+  } else {
+#pragma unroll
+    for (int r = 0; r < kGramCenterRows; ++r) {
+      const float* q = cref + static_cast<int64_t>(r < rows ? r : rows - 1) * ld + col;
+      t[r] = make_float4(col < d ? __ldg(q) : 0.f, col + 1 < d ? __ldg(q + 1) : 0.f, col + 2 < d ? __ldg(q + 2) : 0.f, 0.f);
+    }
+  }
+  float cx = 0.f, cy = 0.f, cz = 0.f, cw = 0.f;
+#pragma unroll
+  for (int r = 0; r < kGramCenterRows; ++r) { cx += t[r].x; cy += t[r].y; cz += t[r].z; cw += t[r].w; }
+  const float inv = 1.0f / static_cast<float>(kGramCenterRows);
+  return make_float4(cx * inv, cy * inv, cz * inv, cw * inv);
+}
+
 
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_inc() {

@@ -202,11 +202,11 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         const int it_begin = g * p.flush, it_end = min(it_begin + p.flush, nkb);
         const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
         int it = it_begin + j;                          // flush is even: parity of `it` == issuer id
-        if (it < it_end) {
-          mbar_wait_fast(&acc_empty[b], gph ^ 1);
-          if (j == 1) mbar_wait_fast(&first_issued[b], gph);
-          tc_fence_after();
-        }
+        // issuer 1 waits for issuer 0's first MMA of the group even when it has no k-block in it (odd tail): its
+        // acc_full commit must not land in the barrier's previous phase
+        if (j == 0) mbar_wait_fast(&acc_empty[b], gph ^ 1);
+        else mbar_wait_fast(&first_issued[b], gph);
+        tc_fence_after();
         for (; it < it_end; it += 2) {
           if (lane == 0) trace_ev(p, it, 11);
           named_bar_sync(1 + s, 32 + 32);               // the split warp owning stage s is done (implies TMA landed)
@@ -464,7 +464,12 @@ __global__ void sqdist_to_dist_kernel(const double* __restrict__ d2, int n, floa
 // streaming bf16x2 kernel (gram_bf16.cu)
 bool bf16x2_eligible(int n, int64_t d);
 int bf16x2_splits(int64_t d);
-int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, int splits, int flush, cudaStream_t stream);
+int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, int splits, int flush, int center, cudaStream_t stream);
+// tile-pair bf16x2 kernel for N > 128 (gram_pair.cu)
+int pair_splits(int n, int64_t d);
+size_t pair_parts_bytes(int n, int64_t d);
+int launch_pair(const float* G, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush, int center,
+                cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -488,6 +493,7 @@ static EncodeTiledFn encode_fn() {
 struct Plan {
   bool tensor;
   bool bf16;          // streaming bf16x2 kernel (gram_bf16.cu) instead of the TMA + split-TF32 kernel
+  bool pair;          // lower-triangular tile-pair bf16x2 kernel (gram_pair.cu), N > 128
   int tiles, splits, stages, stage_bytes, flush, kchunk_log2;
   int simt_splits;
   size_t parts_bytes, s_bytes, total;
@@ -557,6 +563,10 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     pl.flush &= ~1;                                     // even: the two issuers alternate k-blocks
     if (pl.bf16) pl.splits = bf16x2_splits(d);
     pl.parts_bytes = static_cast<size_t>(pairs) * pl.splits * kPartElems * sizeof(float);
+    // N > 128: the triangular bf16x2 tile-pair kernel (AFL_GRAM_TF32X2 / AFL_GRAM_KERNEL=tf32 keeps the round-1
+    // all-ordered-pairs split-TF32 kernel for comparison)
+    pl.pair = n > kTileRows && !(flags & (AFL_GRAM_SINGLE_PASS | AFL_GRAM_TF32X2)) && !(kenv && kenv[0] == 't');
+    if (pl.pair) { pl.splits = pair_splits(n, d); pl.parts_bytes = pair_parts_bytes(n, d); }
     pl.s_bytes = align_up(2 * static_cast<size_t>(n) * n * sizeof(double), 256);
     pl.total = pl.parts_bytes + pl.s_bytes;
   } else {
@@ -593,11 +603,18 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
     return AFL_ERR_WORKSPACE;
   }
   const dim3 rblock(128), rgrid((n + 127) / 128, n);
+  // translation invariance: operands are converted as g - (last client's row) unless switched off
+  const int center = !(flags & AFL_GRAM_NO_CENTER) && env_int("AFL_GRAM_CENTER", 1) != 0;
   if (pl.tensor) {
+    if (pl.pair) {
+      float* parts = static_cast<float*>(ws);
+      double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
+      return launch_pair(static_cast<const float*>(G), n, d, ld, parts, S, d2_out, pl.flush, center, stream);
+    }
     if (pl.bf16) {
       float* parts = static_cast<float*>(ws);
       double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
-      int rc = launch_bf16x2(static_cast<const float*>(G), n, d, ld, parts, pl.splits, pl.flush, stream);
+      int rc = launch_bf16x2(static_cast<const float*>(G), n, d, ld, parts, pl.splits, pl.flush, center, stream);
       if (rc) return rc;
       gram_reduce_kernel<<<dim3(n, 2, 1), dim3(128, kSy), 0, stream>>>(parts, n, 1, pl.splits, S);
       AFL_LAUNCH_CHECK("gram_reduce_kernel");

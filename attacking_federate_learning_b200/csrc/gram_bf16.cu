@@ -43,6 +43,10 @@ struct B16Params {
   int kblocks;          // ceil(d / 64)
   int flush;            // k-blocks per TMEM accumulation chain (even)
   float* parts;         // [splits][2][128][128]
+  int center;           // subtract the last client's row while converting (translation invariance)
+  const float* cref;    // first of the last cref_rows rows
+  int cref_rows; int64_t cref_ld;
+  int64_t d;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
@@ -133,11 +137,11 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
         const int it_begin = g * p.flush, it_end = min(it_begin + p.flush, nkb);
         const uint32_t d_acc = tmem_base + static_cast<uint32_t>(b * 256);
         int it = it_begin + j;
-        if (it < it_end) {
-          mbar_wait_fast(&acc_empty[b], gph ^ 1);
-          if (j == 1) mbar_wait_fast(&first_issued[b], gph);
-          tc_fence_after();
-        }
+        // issuer 1 waits for issuer 0's first MMA of the group even when it has no k-block in it (odd tail): its
+        // acc_full commit must not land in the barrier's previous phase
+        if (j == 0) mbar_wait_fast(&acc_empty[b], gph ^ 1);
+        else mbar_wait_fast(&first_issued[b], gph);
+        tc_fence_after();
         for (; it < it_end; it += 2) {
           named_bar_sync(1 + s, 32 + 32);                // converter warp s has written and fenced stage s
           tc_fence_after();
@@ -184,10 +188,26 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
       lane_off[k] = static_cast<uint32_t>(rsub) * 128u + (static_cast<uint32_t>(c16 & 1) << 3) +
                     (static_cast<uint32_t>((c16 >> 1) ^ ((2 * k + rsub) & 7)) << 4);
     const int full_rows = p.n & ~15;
+    // centre = mean of the last 8 clients over this lane's 4 columns; their rows are part of the k-block that TMA
+    // just delivered, so they are read from shared memory (8 broadcast LDS.128 per k-block) - no extra L2 traffic
+    const int crow0 = p.n >= kGramCenterRows ? p.n - kGramCenterRows : 0;
+    const uint32_t cen_off = static_cast<uint32_t>(c16) * 16u;
     for (int kb = w4; kb < nkb; kb += kBfStages) {
       const uint32_t ph = static_cast<uint32_t>(kb / kBfStages) & 1u;
       mbar_wait_fast(&bf_empty[w4], ph ^ 1);
       mbar_wait_fast(&raw_full[w4], ph);
+      float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.center) {
+        float4 t[kGramCenterRows];
+#pragma unroll
+        for (int r = 0; r < kGramCenterRows; ++r) {
+          const int row = crow0 + r < p.n ? crow0 + r : p.n - 1;
+          t[r] = lds128(src + static_cast<uint32_t>(row) * 256u + cen_off);
+        }
+#pragma unroll
+        for (int r = 0; r < kGramCenterRows; ++r) { cen.x += t[r].x; cen.y += t[r].y; cen.z += t[r].z; cen.w += t[r].w; }
+        cen.x *= 0.125f; cen.y *= 0.125f; cen.z *= 0.125f; cen.w *= 0.125f;
+      }
       // Full 16-row groups, branch-free and software-pipelined: the next group's 8 LDS.128 are issued
       // before this group's 16 STS.64, the 8 independent conversion chains interleave.
       float4 v[8];
@@ -200,10 +220,11 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
         uint32_t h[8][2], l[8][2];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          h[u][0] = pack_bf16x2_rn(v[u].x, v[u].y);
-          h[u][1] = pack_bf16x2_rn(v[u].z, v[u].w);
-          l[u][0] = pack_bf16x2_rn(v[u].x - __uint_as_float(h[u][0] << 16), v[u].y - __uint_as_float(h[u][0] & 0xFFFF0000u));
-          l[u][1] = pack_bf16x2_rn(v[u].z - __uint_as_float(h[u][1] << 16), v[u].w - __uint_as_float(h[u][1] & 0xFFFF0000u));
+          const float x0 = v[u].x - cen.x, x1 = v[u].y - cen.y, x2 = v[u].z - cen.z, x3 = v[u].w - cen.w;
+          h[u][0] = pack_bf16x2_rn(x0, x1);
+          h[u][1] = pack_bf16x2_rn(x2, x3);
+          l[u][0] = pack_bf16x2_rn(x0 - __uint_as_float(h[u][0] << 16), x1 - __uint_as_float(h[u][0] & 0xFFFF0000u));
+          l[u][1] = pack_bf16x2_rn(x2 - __uint_as_float(h[u][1] << 16), x3 - __uint_as_float(h[u][1] & 0xFFFF0000u));
         }
         if (r0 + 16 < full_rows) {
 #pragma unroll
@@ -222,7 +243,8 @@ gram_bf16x2_kernel(const __grid_constant__ CUtensorMap tmap, const B16Params p) 
         for (int u = 0; u < 8; ++u) {
           const int row = full_rows + 2 * u + rsub;
           if (row < p.n) {
-            const float4 t = lds128(src_lane + static_cast<uint32_t>(full_rows + 2 * u) * 256u);
+            float4 t = lds128(src_lane + static_cast<uint32_t>(full_rows + 2 * u) * 256u);
+            t.x -= cen.x; t.y -= cen.y; t.z -= cen.z; t.w -= cen.w;
             const uint32_t h0 = pack_bf16x2_rn(t.x, t.y), h1 = pack_bf16x2_rn(t.z, t.w);
             const uint32_t l0 = pack_bf16x2_rn(t.x - __uint_as_float(h0 << 16), t.y - __uint_as_float(h0 & 0xFFFF0000u));
             const uint32_t l1 = pack_bf16x2_rn(t.z - __uint_as_float(h1 << 16), t.w - __uint_as_float(h1 & 0xFFFF0000u));
@@ -297,7 +319,7 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // parts must hold bf16x2_splits(d) * 2*128*128 floats (gram_reduce_kernel only reads rows/columns < n).
-int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, int splits, int flush,
+int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, int splits, int flush, int center,
                   cudaStream_t stream) {
   static EncodeTiledFn2 enc = nullptr;
   if (!enc) {
@@ -313,6 +335,11 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
   p.flush = flush < 2 ? 2 : (flush & ~1);
   p.splits = splits;
   p.parts = parts;
+  p.center = center ? 1 : 0;
+  p.cref_rows = n < kGramCenterRows ? n : kGramCenterRows;
+  p.cref = G + static_cast<int64_t>(n - p.cref_rows) * ld;
+  p.cref_ld = ld;
+  p.d = d;
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};

@@ -7,6 +7,7 @@ import torch
 
 from . import defences
 from . import _device as dev
+from .ingest import ShardIngest
 
 
 class AggregationServer:
@@ -22,9 +23,15 @@ class AggregationServer:
         self.velocity = torch.zeros(dim, dtype=torch.float32, device=device)   # server.py:36
         self.current_weights = (torch.zeros(dim, dtype=torch.float32, device=device) if initial_weights is None
                                 else torch.as_tensor(initial_weights, dtype=torch.float32).to(device).clone())
+        self._ingest = ShardIngest(self.users_grads) if dtype == torch.float32 else None
 
     def collect_gradients(self, users):
-        """server.py:81-83: users_grads[idx, :] = usr.grads  (rows may come from host or device)."""
+        """server.py:81-83: users_grads[idx, :] = usr.grads.  Host rows are staged through pinned memory on a copy
+        stream (ingest.ShardIngest), so the transfer overlaps whatever the compute stream is still running; device
+        rows are copied device to device.  `defend` waits for the copies."""
+        if self._ingest is not None:
+            self._ingest.collect(users)
+            return
         for idx, usr in enumerate(users):
             g = usr.grads
             if not isinstance(g, torch.Tensor):
@@ -34,6 +41,8 @@ class AggregationServer:
     def defend(self, defence_method, cur_epoch=0):
         """server.py:86-90 (keeps the reference's use of the base learning rate)."""
         n = self.users_count
+        if self._ingest is not None:
+            self._ingest.wait()
         current_grads = defences.defend[defence_method](self.users_grads, n, int(n * self.mal_prop))
         if current_grads.dtype != torch.float32:
             current_grads = current_grads.float()

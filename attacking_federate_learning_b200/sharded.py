@@ -34,6 +34,42 @@ class ShardedAggregator:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._buf = {}
+        self._peer = None                 # PeerContext (NVLink peer-memory exchange) or None
+        self._peer_error = None           # why the peer path is off (then NCCL all-reduce is used)
+
+    # -- NVLink peer-memory exchange (csrc/xgpu.cu); falls back to the NCCL all-reduce if it cannot be set up
+    def _peer_context(self, n, device):
+        if self._peer_error is not None or not hasattr(self.k, "PeerContext"):
+            return None
+        if self._peer is not None and self._peer.n_max >= n:
+            return self._peer
+        ok = 1
+        ctx = None
+        try:
+            if self._peer is not None:
+                self._peer.close(); self._peer = None
+            ctx = self.k.PeerContext(self.world, self.rank, max(n, 128), device)
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, ctx.handle(), group=self.group)
+                ctx.connect(handles)
+        except Exception as ex:          # pragma: no cover - depends on the box (IPC permissions, peer access)
+            ok = 0
+            self._peer_error = repr(ex)[:300]
+        if self.world > 1:                # every rank must take the same path
+            flag = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok = int(flag.item())
+        if not ok:
+            self._peer_error = self._peer_error or "a peer rank could not map the exchange buffers"
+            if ctx is not None:
+                try:
+                    ctx.close()
+                except Exception:
+                    pass
+            return None
+        self._peer = ctx
+        return ctx
 
     # -- the single exchange step of the path
     def _allreduce_table(self, d2):
@@ -54,8 +90,13 @@ class ShardedAggregator:
     def krum(self, G_shard, users_count, corrupted_count, return_index=False):
         if not return_index:
             assert users_count >= 2 * corrupted_count + 1, ('users_count>=2*corrupted_count + 3', users_count, corrupted_count)
-        if hasattr(self.k, "krum_from_sqdist"):
-            # hot path: two FFI crossings + the one all-reduce, persistent buffers, one 4-byte D2H sync
+        peer = self._peer_context(G_shard.shape[0], G_shard.device) if G_shard.is_cuda else None
+        if peer is not None:
+            # hot path: ONE FFI crossing: Gram -> publish -> fused tail (peer-memory sum, sqrt, sort, score, argmin),
+            # index through mapped pinned memory, one stream synchronisation
+            idx = peer.krum(G_shard, users_count, corrupted_count)
+        elif hasattr(self.k, "krum_from_sqdist"):
+            # two FFI crossings + the NCCL all-reduce, persistent buffers, one 4-byte D2H sync
             d2, idx_dev = self._buffers(G_shard.shape[0], G_shard.device)
             self.k.sqdist_partial(G_shard, 0, d2)
             self._allreduce_table(d2)
@@ -66,7 +107,13 @@ class ShardedAggregator:
 
     def bulyan(self, G_shard, users_count, corrupted_count, return_selection=False):
         assert users_count >= 4 * corrupted_count + 3
-        sel = self.k.bulyan_select(self.distances(G_shard), users_count, corrupted_count)
+        peer = self._peer_context(G_shard.shape[0], G_shard.device) if (G_shard.is_cuda and self.world > 1) else None
+        if peer is not None:
+            d2, _ = self._buffers(G_shard.shape[0], G_shard.device)
+            table = self.k.sqdist_to_dist(peer.allreduce_table(G_shard, d2))
+        else:
+            table = self.distances(G_shard)
+        sel = self.k.bulyan_select(table, users_count, corrupted_count)
         out = self.k.trimmed_mean(G_shard, 2 * corrupted_count, row_index=sel)
         if len(sel) and int(sel[-1]) < 0:                # no eligible user in some round: defences.py:66 raises KeyError(-1)
             raise KeyError(-1)
@@ -88,7 +135,11 @@ class ShardedAggregator:
         return crafted
 
     def exchange_name(self):
-        return "NCCL all-reduce" if self.world > 1 else "none"
+        if self.world == 1:
+            return "none"
+        if self._peer is not None:
+            return "NVLink peer-memory sum inside the fused tail kernel (csrc/xgpu.cu)"
+        return "NCCL all-reduce" + (f" (peer path off: {self._peer_error})" if self._peer_error else "")
 
     def defend(self, name, G_shard, users_count, corrupted_count):
         return {"Krum": self.krum, "TrimmedMean": self.trimmed_mean, "NoDefense": self.no_defense,

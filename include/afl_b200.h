@@ -57,6 +57,8 @@ enum {
   AFL_GRAM_SINGLE_PASS = 4,   /* tcgen05: hi*hi only (plain TF32), for measurement                  */
   AFL_GRAM_TF32X2 = 16,       /* tcgen05: always the TMA + split-TF32 kernel (default outside the bf16x2 range) */
   AFL_GRAM_BF16X2 = 32,       /* tcgen05: bf16x2 kernel (gram_bf16.cu), the default when 64<=N_pad<=112, D>=32768 */
+  AFL_GRAM_NO_CENTER = 64,    /* bf16x2 kernels: do not subtract the last client's row while converting (the  */
+                              /* default makes the table translation invariant; env AFL_GRAM_CENTER=0 too)    */
   AFL_GRAM_REWRITE_HI = 8     /* accepted, ignored (kind::tf32 was measured to ignore the low 13     */
                               /* mantissa bits of fp32 operands, which is what the split relies on)  */
 };
@@ -82,8 +84,9 @@ int afl_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, float* out,
 
 /* ---- pairwise squared distances:  defences.py:16-21  _krum_create_distances ------------------- */
 /* Partial squared L2 distances over this shard's d columns, as a dense symmetric n x n float64
- * table (zero diagonal).  fp32 inputs, AFL_GRAM_AUTO: G*G^T on tcgen05 tensor cores (TMA-fed,
- * split-TF32, TMEM accumulators), d2_ij = s_ii + s_jj - 2 s_ij.  Partial tables of different shards
+ * table (zero diagonal).  fp32 inputs, AFL_GRAM_AUTO: G*G^T on tcgen05 tensor cores (TMA-fed, bf16x2 or
+ * split-TF32 operands, TMEM accumulators; n > 128: lower-triangular 128 x 128 tile pairs), d2_ij =
+ * s_ii + s_jj - 2 s_ij on rows centred on the last client's row.  Partial tables of different shards
  * ADD; take the square root only after the all-reduce (afl_sqdist_to_dist). */
 size_t afl_sqdist_workspace_bytes(int n, int64_t d, int dtype, int flags);
 int afl_sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out,
@@ -123,6 +126,10 @@ int afl_bulyan_select(const float* dist, int n, int users_count, int corrupted_c
 int afl_trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* row_index,
                      int n_rows, int corrupted_count, float* out, void* stream);
 
+/* Diagnostics of the packed bf16 kernel (synchronises the device): out4 = {unused, columns handed to the general
+ * per-column path, bracket retries, unused}; reset != 0 clears the counters. */
+int afl_debug_tm_stats(unsigned long long* out4, int reset);
+
 /* ---- gather one row chosen on the device (Krum's result as a dense vector) --------------------- */
 int afl_gather_row(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* idx_dev,
                    float* out, void* stream);
@@ -149,6 +156,26 @@ int afl_alie_band(const float* mu, const float* sigma, double z, const float* x,
  * v = momentum*v - lr*g ;  w += v   (fp32, in place). */
 int afl_momentum_step(float* weights, float* velocity, const float* grads, int64_t d, float momentum,
                       float learning_rate, void* stream);
+
+/* ---- multi-GPU exchange over NVLink peer memory ("exactly one sum of the n x n partial table") ------
+ * One process per GPU.  Every rank creates a context, exports its 64-byte CUDA IPC handle, the host layer gathers
+ * the handles of all ranks (any transport) and every rank maps its peers.  world == 1 needs no connect.
+ *   afl_krum_sharded     partial table of this rank's [n, d_local] shard (afl_sqdist_partial) -> published to the peers ->
+ *                        fused tail: sum of the ranks' tables in rank order, sqrt, per-client sort, Krum score, argmin
+ *                        (defences.py:16-42).  Enqueues only.  After `stream` is synchronised *idx_host_out (mapped
+ *                        pinned memory) holds the index (identical on every rank), *status_host_out is 0 (1: a peer did
+ *                        not publish in time) and *idx_dev_out is the device copy (for afl_gather_row).
+ *   afl_sqdist_allreduce the same exchange, result = the summed table in d2_total (device, n*n float64) for callers
+ *                        that run their own selection (Bulyan). */
+int afl_xgpu_create(int world, int rank, int n_max, void** ctx_out);
+int afl_xgpu_handle(void* ctx, unsigned char* out64);
+int afl_xgpu_connect(void* ctx, const unsigned char* handles /* world x 64 bytes, rank order */);
+int afl_xgpu_destroy(void* ctx);
+int afl_krum_sharded(void* ctx, const void* G, int n, int64_t d, int64_t ld, int dtype, int users_count, int corrupted_count,
+                     void* workspace, size_t workspace_bytes, int flags, void* stream, int** idx_host_out,
+                     int** status_host_out, int** idx_dev_out);
+int afl_sqdist_allreduce(void* ctx, const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_total, void* workspace,
+                         size_t workspace_bytes, int flags, void* stream, int** status_host_out);
 
 /* ---- one-call host-buffer API (what a cgo/ctypes binding of server.py:87 would call) ----------
  * rule: "NoDefense" | "Krum" | "TrimmedMean" | "Bulyan" (defences.py:4-8).  G_host: n x d fp32 in

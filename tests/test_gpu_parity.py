@@ -206,11 +206,15 @@ def test_krum_matches_oracle(api, n, d, f, seed):
     Gp = torch.zeros((n, (d + 3) // 4 * 4), device="cuda")[:, :d]; Gp.copy_(Gd)
     off = ~np.eye(n, dtype=bool)
     ref2 = (table64 ** 2)[off]
-    for flags, bias_cap in ((nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2, 6e-6), (nat.GRAM_FORCE_TCGEN05 | nat.GRAM_TF32X2, 2e-6)):
+    # bf16x2 kernels convert g - c (c = mean of the last 8 clients): the bias scales with ||g_i - c||^2 + ||g_j - c||^2
+    # (~ d2 times 1..1.5 here), hence a pair-to-pair spread of ~2e-6 in d2 (1e-6 in the distance), still an order below the 1e-5 margin rule.
+    for flags, bias_cap, spread_cap in ((nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2, 8e-6, 3e-6),
+                                        (nat.GRAM_FORCE_TCGEN05 | nat.GRAM_BF16X2 | nat.GRAM_NO_CENTER, 6e-6, 5e-7 if n <= 112 else 2e-6),
+                                        (nat.GRAM_FORCE_TCGEN05 | nat.GRAM_TF32X2, 2e-6, 5e-7)):
         d2 = dev.sqdist_partial(Gp, flags).cpu().numpy()
         rel = (d2[off] - ref2) / ref2
         assert np.abs(rel).max() < bias_cap, np.abs(rel).max()
-        assert rel.max() - rel.min() < 5e-7, (rel.min(), rel.max())
+        assert rel.max() - rel.min() < spread_cap, (rel.min(), rel.max())
         assert np.array_equal(d2, d2.T) and not d2.diagonal().any()
     d2s = dev.sqdist_partial(Gd, nat.GRAM_FORCE_SIMT).cpu().numpy()
     assert (np.abs(d2s[off] - ref2) / ref2).max() < 1e-6
@@ -339,3 +343,32 @@ def test_properties_at_scale(api):
     assert torch.equal(D.trimmed_mean(C, n2, 240), torch.full((4096,), 3.25, device="cuda"))
     cols = torch.arange(0, d2c, 397, device="cuda")
     close(tm[cols].cpu().numpy(), orc.trimmed_mean(X[:, cols].cpu().numpy(), n2, 240), 0.8)
+
+
+def test_harness_epoch_loop_writes_reference_outputs(api, tmp_path):
+    """main.py:64-100 equivalent on the device-resident matrix: accuracy CSV (main.py:100) and checkpoint dict (main.py:85-89)."""
+    from attacking_federate_learning_b200 import harness
+    acc, epochs, csv = harness.main(0.24, 1.5, 'Krum', users_count=10, epochs=16, learning_rate=0.1, batch_size=128,
+                                    out_dir=str(tmp_path), train_size=6000, test_size=1500, output=str(tmp_path / "log.txt"))
+    assert epochs == [0, 5, 10, 15] and len(acc) == 4
+    assert np.allclose(np.loadtxt(csv, delimiter=','), acc)
+    assert acc[-1] > acc[0] + 20.0                                   # it learns under attack with Krum
+    if max(acc) > 70.0:
+        ck = torch.load(tmp_path / "runs" / harness.SYNTH / "checkpoint.pth.tar", weights_only=False)
+        assert set(ck) == {'epoch', 'state_dict', 'acc'} and 'fc1.weight' in ck['state_dict']
+
+
+def test_server_ingest_overlaps_and_matches(api):
+    """collect_gradients through the pinned staging path (host rows) and device rows give the same matrix."""
+    from attacking_federate_learning_b200.server import AggregationServer
+    rng = np.random.default_rng(9)
+    n, d = 37, 12345
+    G = hetero(rng, n, d)
+
+    class U:
+        def __init__(self, g): self.grads = g
+    srv = AggregationServer(n, d, mal_prop=0.2, learning_rate=0.1)
+    srv.collect_gradients([U(G[i]) if i % 3 else U(torch.from_numpy(G[i]).cuda()) for i in range(n)])
+    out = srv.defend('NoDefense')
+    assert np.array_equal(srv.users_grads.cpu().numpy(), G)
+    np.testing.assert_array_equal(out.cpu().numpy(), orc.no_defense(G))

@@ -29,8 +29,21 @@ res["bulyan_out"] = bool(torch.equal(out, ref_out[c0:c1]))
 res["tm"] = bool(torch.equal(agg.trimmed_mean(shard, n, f), D.trimmed_mean(full, n, f)[c0:c1]))
 gathered = agg.gather_output(out, d)
 res["gather"] = bool(torch.equal(gathered, ref_out))
+res["exchange"] = agg.exchange_name()
+# C4-like client count through the tile-pair kernel and the peer-memory exchange (reduced D)
+n2, d2, f2 = 500, 262144, 100
+g2 = torch.Generator(device="cuda").manual_seed(11)
+full2 = torch.exp(0.25 * torch.randn(n2, 1, generator=g2, device="cuda")) * torch.randn(n2, d2, generator=g2, device="cuda")
+a0, a1 = shard_bounds(d2, world, rank)
+sh2 = full2[:, a0:a1].contiguous()
+o2, s2 = agg.bulyan(sh2, n2, f2, return_selection=True)
+r2, rs2 = D.bulyan(full2, n2, f2, return_selection=True)
+res["bulyan500_sel"] = bool(torch.equal(s2, rs2))
+res["bulyan500_out"] = bool(torch.allclose(o2, r2[a0:a1], rtol=1e-5, atol=1e-6))
+res["krum500"] = [agg.krum(sh2, n2, f2, return_index=True), D.krum(full2, n2, f2, return_index=True)]
 flags = torch.tensor([int(res["alie"]), int(res["krum"][0] == res["krum"][1]), int(res["bulyan_sel"]),
-                      int(res["bulyan_out"]), int(res["tm"]), int(res["gather"])], device="cuda")
+                      int(res["bulyan_out"]), int(res["tm"]), int(res["gather"]), int(res["bulyan500_sel"]),
+                      int(res["bulyan500_out"]), int(res["krum500"][0] == res["krum500"][1])], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("MULTIGPU " + json.dumps({"world": world, "all_ranks_ok": flags.tolist(), "rank0": res}))

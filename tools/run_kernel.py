@@ -19,6 +19,14 @@ elif what == "gram":
     G = torch.randn(100, 11_200_000, generator=g, device="cuda")
     for _ in range(iters):
         dev.sqdist_partial(G)
+elif what == "pair1000":
+    G = torch.randn(1000, 1 << 19, generator=g, device="cuda")
+    for _ in range(iters):
+        dev.sqdist_partial(G)
+elif what == "pair500":
+    G = torch.randn(500, 2_500_000 // 32 * 32, generator=g, device="cuda")
+    for _ in range(iters):
+        dev.sqdist_partial(G)
 elif what == "gram500":
     G = torch.randn(500, 1 << 20, generator=g, device="cuda")
     for _ in range(iters):
