@@ -6,15 +6,14 @@
 //     k-blocks s, s+S, s+2S, ... and writes its partial [hh | X] tile to a private slot, which
 //     pair_reduce_kernel sums in a fixed order in float64 (bit-reproducible).
 //   * One TMA box {64 fp32 columns x 128 rows} (32 KB, no swizzle, OOB rows/columns zero-filled) per tile and
-//     k-block lands in a 6-slot shared-memory ring (tools/tma_bench.cu: ~450 ns per box per SM whatever it
+//     k-block lands in a 7-slot shared-memory ring (tools/tma_bench.cu: ~450 ns per box per SM whatever it
 //     holds, so boxes must be this large).  A converter warp then rewrites the slot IN PLACE: every 8-row unit
 //     (2 KB of fp32) becomes one SWIZZLE_128B core-matrix atom of b1 (1 KB) followed by one of b2 (1 KB), with
 //     g - c = b1 + b2 + r, |r| <= 2^-17 |g - c| (both roundings to nearest), c = the mean of the LAST 8 clients' rows
 //     (translation invariance of the distances: the cancellation error of d2 = s_ii + s_jj - 2 s_ij then
 //     scales with the distances to an honest client - main.py:28 makes ids >= f honest - instead of with
 //     ||g||^2).  A unit's output only overwrites that unit's own input, which the warp has already loaded, so
-//     there is no second staging buffer: 6 x 32 KB of shared memory hold 3 k-blocks in flight.  The I tile comes by TMA,
-//     the J tile by cp.async from a second producer warp (the TMA unit needs ~450-600 ns per box).
+//     there is no second staging buffer: 7 x 32 KB of shared memory hold 3.5 k-blocks in flight.
 //   * Operands are K-major with an 8-row-group stride (SBO) of 2048 bytes: b1 tile at slot + 0, b2 tile at
 //     slot + 1024.  Per 16 columns three tcgen05.mma.kind::f16 (M = 128, N = 128, K = 16):
 //         hh += b1_I b1_J^T        X += b1_I b2_J^T        X += b2_I b1_J^T
@@ -25,8 +24,8 @@
 //   * TMEM: two accumulator buffers of 256 columns ([hh | X]), drained every `flush` k-blocks by 8 epilogue
 //     warps into fp32 registers (the tensor core truncates while accumulating; chains stay short).
 //
-// Warp roles (512 threads): warp 0 TMA producer (I tile), warps 1,3 MMA issue (alternating k-blocks), warp 2 TMEM
-// alloc + cp.async producer (J tile), warps 4-7 converters (warp w owns boxes w, w+4, ...), warps 8-15 epilogue.
+// Warp roles (512 threads): warp 0 TMA producer, warps 1,3 MMA issue (alternating k-blocks), warp 2 TMEM
+// alloc, warps 4-7 converters (warp w owns boxes w, w+4, ...), warps 8-15 epilogue.
 // bounded waits trap after 2^35 cycles (~18 s) here: profiler replays with patched SASS run this kernel >100x slower
 #define AFL_BAR_TIMEOUT_LOG2 35
 #include "afl_common.cuh"
@@ -35,7 +34,10 @@ namespace afl {
 namespace gram {
 
 constexpr int kPThreads = 512;
-constexpr int kPSlots = 6;                   // 32 KB slots: one box = one tile's k-block (even: I tiles / TMA, odd: J tiles / cp.async)
+// J tile by cp.async (LDGSTS) from warp 2 instead of a second TMA box per k-block: measured 2.3x SLOWER than two TMA
+// boxes (r02 run E: 6.2 ms vs 2.7 ms at N = 1000, D = 524,288), kept behind this switch for the record.
+constexpr bool kJByCpAsync = false;
+constexpr int kPSlots = kJByCpAsync ? 6 : 7;   // 32 KB slots: one box = one tile's k-block
 constexpr int kPSlotBytes = 128 * 256;       // 128 rows x 64 fp32
 constexpr int kPCols = 64;                   // columns per k-block
 constexpr int kPPartElems = 2 * 128 * 128;   // [hh | X] per (pair, split)
@@ -107,11 +109,11 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
   // (TMA, one expect_tx arrival) in even slots and the J tile (cp.async, one arrival per lane) in odd slots: the TMA
   // unit then moves ONE box per k-block (it needs ~450-600 ns per box whatever the box holds, more than the ~680 ns of
   // tensor work per k-block would leave for two), the other 32 KB go through the LSU path.
-  auto slot_of = [&](int b) -> int { return has_b ? ((b >> 1) % 3) * 2 + (b & 1) : b % kPSlots; };
-  auto phase_of = [&](int b) -> uint32_t { return static_cast<uint32_t>(has_b ? ((b >> 1) / 3) : (b / kPSlots)) & 1u; };
+  auto slot_of = [&](int b) -> int { return (kJByCpAsync && has_b) ? ((b >> 1) % 3) * 2 + (b & 1) : b % kPSlots; };
+  auto phase_of = [&](int b) -> uint32_t { return static_cast<uint32_t>((kJByCpAsync && has_b) ? ((b >> 1) / 3) : (b / kPSlots)) & 1u; };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kPSlots; ++s) { mbar_init(&raw_full[s], (has_b && (s & 1)) ? 32 : 1); mbar_init(&slot_free[s], 1); }
+    for (int s = 0; s < kPSlots; ++s) { mbar_init(&raw_full[s], (kJByCpAsync && has_b && (s & 1)) ? 32 : 1); mbar_init(&slot_free[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 2);
       mbar_init(&acc_empty[b], 8);
@@ -136,16 +138,19 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
       if (lane == 0) {
         const uint64_t pol = policy_evict_normal();       // every row tile is read by T CTAs: keep it in L2
         for (int i = 0; i < nkb; ++i) {
-          const int b = i * nbx;
-          const int s = slot_of(b);
-          mbar_wait(&slot_free[s], phase_of(b) ^ 1u);
-          mbar_arrive_expect_tx(&raw_full[s], kPSlotBytes);
-          tma_load_2d(smem + static_cast<size_t>(s) * kPSlotBytes, &tmap, &raw_full[s], (split + i * p.splits) * kPCols, ti * 128, pol);
+          for (int t = 0; t < ((kJByCpAsync || !has_b) ? 1 : 2); ++t) {
+            const int b = i * nbx + t;
+            const int s = slot_of(b);
+            mbar_wait(&slot_free[s], phase_of(b) ^ 1u);
+            mbar_arrive_expect_tx(&raw_full[s], kPSlotBytes);
+            tma_load_2d(smem + static_cast<size_t>(s) * kPSlotBytes, &tmap, &raw_full[s], (split + i * p.splits) * kPCols,
+                        (t == 0 ? ti : tj) * 128, pol);
+          }
         }
       }
     } else if (warp == 2) {
       // ===================== J-tile producer: cp.async (LDGSTS), 16 bytes per lane, zero fill past d =====================
-      if (has_b) {
+      if (kJByCpAsync && has_b) {
         const float* gj = p.G + static_cast<int64_t>(tj) * 128 * p.ld;    // tj < ti: the J tile always has 128 rows
         for (int i = 0; i < nkb; ++i) {
           const int b = 2 * i + 1;

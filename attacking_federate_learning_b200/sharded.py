@@ -9,6 +9,8 @@ The per-shard arithmetic is delegated to a `kernels` object; the default binds t
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -39,6 +41,8 @@ class ShardedAggregator:
 
     # -- NVLink peer-memory exchange (csrc/xgpu.cu); falls back to the NCCL all-reduce if it cannot be set up
     def _peer_context(self, n, device):
+        if self._peer_error is None and os.environ.get("AFL_XGPU", "1") == "0":
+            self._peer_error = "disabled by AFL_XGPU=0"
         if self._peer_error is not None or not hasattr(self.k, "PeerContext"):
             return None
         if self._peer is not None and self._peer.n_max >= n:
