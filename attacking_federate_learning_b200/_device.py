@@ -199,15 +199,33 @@ class PeerContext:
             self.ctx = _C.c_void_p()
 
     def krum(self, G: torch.Tensor, users_count: int, corrupted_count: int, flags: int = 0) -> int:
-        """Enqueue gram -> publish -> fused tail, synchronise the stream once, return the index."""
-        n, d, ld = check_matrix(G)
-        L = nat.lib()
-        with torch.cuda.device(G.device):
-            ws = Workspace.get(G.device, "gram", L.afl_sqdist_workspace_bytes(n, d, dtype_code(G), flags))
-            nat.check(L.afl_krum_sharded(self.ctx, G.data_ptr(), n, d, ld, dtype_code(G), users_count, corrupted_count,
-                                         ws.data_ptr(), ws.numel(), flags, _stream_ptr(G), _C.byref(self._idx),
-                                         _C.byref(self._status), _C.byref(self._idx_dev)))
-            torch.cuda.current_stream(G.device).synchronize()
+        """Enqueue gram -> publish -> fused tail, synchronise the stream once, return the index.
+        (The per-shape plumbing - workspace, dtype code, bound C function - is cached: this is the per-step hot path.)"""
+        key = (G.data_ptr(), G.shape, G.stride(0), G.dtype, flags)
+        plan = self._plan if getattr(self, "_plan_key", None) == key else None
+        if plan is None:
+            n, d, ld = check_matrix(G)
+            L = nat.lib()
+            with torch.cuda.device(G.device):
+                ws = Workspace.get(G.device, "gram", L.afl_sqdist_workspace_bytes(n, d, dtype_code(G), flags))
+            plan = (L.afl_krum_sharded, n, d, ld, dtype_code(G), ws, _C.byref(self._idx), _C.byref(self._status),
+                    _C.byref(self._idx_dev))
+            self._plan, self._plan_key = plan, key
+        fn, n, d, ld, dt, ws, pidx, pst, pdev = plan
+        same_dev = torch.cuda.current_device() == G.device.index
+        if not same_dev:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(G.device)
+        try:
+            stream = torch.cuda.current_stream(G.device)
+            rc = fn(self.ctx, G.data_ptr(), n, d, ld, dt, users_count, corrupted_count, ws.data_ptr(), ws.numel(), flags,
+                    stream.cuda_stream, pidx, pst, pdev)
+            if rc:
+                nat.check(rc)
+            stream.synchronize()
+        finally:
+            if not same_dev:
+                torch.cuda.set_device(prev)
         if self._status[0] != 0:
             raise RuntimeError("afl_krum_sharded: a peer rank did not publish its partial table in time")
         return int(self._idx[0])

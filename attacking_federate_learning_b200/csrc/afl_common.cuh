@@ -50,6 +50,16 @@ static inline cudaError_t ensure_dyn_smem(K kernel, int bytes, int (&done)[kMaxD
   return e;
 }
 
+// Optional tail of the split reduction (csrc/xgpu.cu): the LAST block to finish also forms the squared-distance
+// table and publishes this rank's epoch flag to every peer, which saves two launches per multi-GPU Krum step.
+constexpr int kMaxWorld = 16;
+struct PubHook {
+  unsigned long long* flag[kMaxWorld];   // flags block of every rank (peer-mapped)
+  int world, rank;
+  unsigned long long epoch;
+  unsigned int* counter;                 // zero-initialised, reset by the last block
+};
+
 // Optional CUDA-event bracket around a kernel launch (active only after afl_profile_enable(1)).
 struct ProfScope {
   ProfScope(const char* name, cudaStream_t stream);

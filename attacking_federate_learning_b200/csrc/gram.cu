@@ -362,6 +362,59 @@ gram_reduce_kernel(const float* __restrict__ parts, int n, int tiles, int splits
   }
 }
 
+// gram_reduce_kernel + gram_to_sqdist_kernel (+ the publish of csrc/xgpu.cu) in one launch, single-tile tables only:
+// every block reduces its row as above; the last block to finish (atomic counter) forms d2 and stores the epoch flag
+// into every peer's flag block.
+__global__ void __launch_bounds__(128 * kSy)
+gram_reduce_d2_kernel(const float* __restrict__ parts, int n, int splits, double* HX, double* __restrict__ d2, const PubHook hook) {
+  __shared__ double sh[kSy][128];
+  __shared__ int s_last;
+  const int i = blockIdx.x, a = blockIdx.y;
+  const int jj = threadIdx.x, sy = threadIdx.y;
+  const float* base = parts + static_cast<size_t>(a) * kTileRows * kTileRows + i * kTileRows + jj;
+  const int s0 = splits * sy / kSy, s1 = splits * (sy + 1) / kSy;
+  double acc = 0.0;
+  if (jj < n)
+    for (int s = s0; s < s1; ++s) acc += static_cast<double>(base[static_cast<size_t>(s) * kPartElems]);
+  sh[sy][jj] = acc;
+  __syncthreads();
+  if (sy == 0 && jj < n) {
+    double t = sh[0][jj];
+#pragma unroll
+    for (int y = 1; y < kSy; ++y) t += sh[y][jj];
+    HX[(static_cast<size_t>(a) * n + i) * n + jj] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * 128 + threadIdx.x;
+  if (tid == 0) s_last = (atomicAdd(hook.counter, 1u) == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* H = HX;
+  const double* X = HX + static_cast<size_t>(n) * n;
+  for (int e = tid; e < n * n; e += 128 * kSy) {
+    const int r = e / n, c = e - r * n;
+    double v = 0.0;
+    if (r != c) {
+      const int lo = min(r, c), hi = max(r, c);
+      const size_t ll = static_cast<size_t>(lo) * n + lo, hh = static_cast<size_t>(hi) * n + hi;
+      const size_t lh = static_cast<size_t>(lo) * n + hi, hl = static_cast<size_t>(hi) * n + lo;
+      const double s_ll = __ldcg(H + ll) + (__ldcg(X + ll) + __ldcg(X + ll));
+      const double s_hh = __ldcg(H + hh) + (__ldcg(X + hh) + __ldcg(X + hh));
+      const double s_lh = __ldcg(H + lh) + (__ldcg(X + lh) + __ldcg(X + hl));
+      v = (s_ll + s_hh) - 2.0 * s_lh;
+    }
+    d2[e] = v;
+  }
+  __syncthreads();
+  if (tid == 0) *hook.counter = 0u;
+  if (hook.world > 1 && tid < hook.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hook.flag[tid] + hook.rank), "l"(hook.epoch) : "memory");
+  }
+}
+
 // d2_ij = s_ii + s_jj - 2 s_ij with s_ij = hh_ij + (x_ij + x_ji); x_ij + x_ji is commutative, so s (and d2)
 // are exactly symmetric, and identical rows give exact zeros.
 __global__ void gram_to_sqdist_kernel(const double* __restrict__ HX, int n, double* __restrict__ d2) {
@@ -589,8 +642,17 @@ size_t workspace_bytes(int n, int64_t d, int dtype, int flags) {
   return (a.total > b.total ? a.total : b.total) + 256;
 }
 
+int sqdist_partial_ex(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out, void* ws, size_t ws_bytes,
+                      int flags, cudaStream_t stream, const PubHook* hook, bool* hook_done);
 int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out, void* ws, size_t ws_bytes,
                    int flags, cudaStream_t stream) {
+  return sqdist_partial_ex(G, n, d, ld, dtype, d2_out, ws, ws_bytes, flags, stream, nullptr, nullptr);
+}
+// hook != null: the caller (csrc/xgpu.cu) wants its epoch flag published once d2_out is complete; *hook_done tells
+// whether the reduction kernel did it (single-tile bf16x2 path) or the caller still has to launch its publish kernel.
+int sqdist_partial_ex(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out, void* ws, size_t ws_bytes,
+                      int flags, cudaStream_t stream, const PubHook* hook, bool* hook_done) {
+  if (hook_done) *hook_done = false;
   if (!G || !d2_out || n < 1 || d < 1 || ld < d) { set_error("afl_sqdist_partial: bad argument"); return AFL_ERR_BAD_ARG; }
   if (dtype != AFL_F32 && dtype != AFL_BF16) { set_error("afl_sqdist_partial: dtype"); return AFL_ERR_UNSUPPORTED; }
   Plan pl = make_plan(G, n, d, ld, dtype, flags);
@@ -616,6 +678,12 @@ int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, doubl
       double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
       int rc = launch_bf16x2(static_cast<const float*>(G), n, d, ld, parts, pl.splits, pl.flush, center, stream);
       if (rc) return rc;
+      if (hook && hook->counter) {
+        gram_reduce_d2_kernel<<<dim3(n, 2, 1), dim3(128, kSy), 0, stream>>>(parts, n, pl.splits, S, d2_out, *hook);
+        AFL_LAUNCH_CHECK("gram_reduce_d2_kernel");
+        if (hook_done) *hook_done = true;
+        return AFL_OK;
+      }
       gram_reduce_kernel<<<dim3(n, 2, 1), dim3(128, kSy), 0, stream>>>(parts, n, 1, pl.splits, S);
       AFL_LAUNCH_CHECK("gram_reduce_kernel");
       gram_to_sqdist_kernel<<<rgrid, rblock, 0, stream>>>(S, n, d2_out);

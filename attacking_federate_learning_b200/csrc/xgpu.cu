@@ -25,10 +25,10 @@ namespace afl {
 namespace gram {
 int sqdist_partial(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out, void* ws, size_t ws_bytes,
                    int flags, cudaStream_t stream);
+int sqdist_partial_ex(const void* G, int n, int64_t d, int64_t ld, int dtype, double* d2_out, void* ws, size_t ws_bytes,
+                      int flags, cudaStream_t stream, const PubHook* hook, bool* hook_done);
 }
 namespace xgpu {
-
-constexpr int kMaxWorld = 16;
 
 struct Ctx {
   int world, rank, n_max, device;
@@ -251,6 +251,15 @@ static double* table_of(const Ctx* c, int r, unsigned long long epoch) {
   return reinterpret_cast<double*>(c->peer[r] + (epoch & 1ull) * c->table_bytes);
 }
 
+// the same flags as a PubHook for the reduction kernel's last block (counter: second word after the done counter)
+static PubHook make_hook(Ctx* c) {
+  PubHook h{};
+  for (int r = 0; r < c->world; ++r) h.flag[r] = reinterpret_cast<unsigned long long*>(c->peer[r] + flags_offset(c));
+  h.world = c->world; h.rank = c->rank; h.epoch = c->epoch;
+  h.counter = reinterpret_cast<unsigned int*>(c->block + flags_offset(c) + sizeof(unsigned long long) * kMaxWorld) + 4;
+  return h;
+}
+
 static int publish(Ctx* c, cudaStream_t stream) {
   if (c->world == 1) return AFL_OK;
   PublishParams pp{};
@@ -277,10 +286,14 @@ int krum_step(void* ctx, const void* G, int n, int64_t d, int64_t ld, int dtype,
   if (c->device != current_device()) { set_error("afl_krum_sharded: context belongs to device %d", c->device); return AFL_ERR_BAD_ARG; }
   c->epoch += 1;
   double* mine = table_of(c, c->rank, c->epoch);
-  int rc = gram::sqdist_partial(G, n, d, ld, dtype, mine, ws, ws_bytes, flags, stream);
+  const PubHook hook = make_hook(c);
+  bool published = false;
+  int rc = gram::sqdist_partial_ex(G, n, d, ld, dtype, mine, ws, ws_bytes, flags, stream, &hook, &published);
   if (rc) return rc;
-  rc = publish(c, stream);
-  if (rc) return rc;
+  if (!published) {
+    rc = publish(c, stream);
+    if (rc) return rc;
+  }
   TailParams tp{};
   for (int r = 0; r < c->world; ++r) tp.tab[r] = table_of(c, r, c->epoch);
   tp.flags = reinterpret_cast<const unsigned long long*>(c->block + flags_offset(c));
@@ -309,10 +322,14 @@ int sqdist_allreduce(void* ctx, const void* G, int n, int64_t d, int64_t ld, int
   if (c->device != current_device()) { set_error("afl_sqdist_allreduce: context belongs to device %d", c->device); return AFL_ERR_BAD_ARG; }
   if (c->world == 1) return gram::sqdist_partial(G, n, d, ld, dtype, d2_total, ws, ws_bytes, flags, stream);
   c->epoch += 1;
-  int rc = gram::sqdist_partial(G, n, d, ld, dtype, table_of(c, c->rank, c->epoch), ws, ws_bytes, flags, stream);
+  const PubHook hook = make_hook(c);
+  bool published = false;
+  int rc = gram::sqdist_partial_ex(G, n, d, ld, dtype, table_of(c, c->rank, c->epoch), ws, ws_bytes, flags, stream, &hook, &published);
   if (rc) return rc;
-  rc = publish(c, stream);
-  if (rc) return rc;
+  if (!published) {
+    rc = publish(c, stream);
+    if (rc) return rc;
+  }
   SumParams sp{};
   for (int r = 0; r < c->world; ++r) sp.tab[r] = table_of(c, r, c->epoch);
   sp.flags = reinterpret_cast<const unsigned long long*>(c->block + flags_offset(c));
