@@ -521,8 +521,8 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
 // tile-pair bf16x2 kernel for N > 128 (gram_pair.cu)
 int pair_splits(int n, int64_t d);
 size_t pair_parts_bytes(int n, int64_t d);
-int launch_pair(const float* G, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush, int center,
-                cudaStream_t stream);
+int launch_pair(const void* G, int dtype, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush,
+                int center, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -558,8 +558,9 @@ static int env_int(const char* name, int dflt) {
 }
 
 static bool tensor_eligible(const void* G, int n, int64_t d, int64_t ld, int dtype) {
-  return dtype == AFL_F32 && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(G) % 16 == 0) && n >= 1 && d >= 1 &&
-         n <= 4096 && d < (int64_t(1) << 31) - 64;
+  const int64_t per16 = dtype == AFL_F32 ? 4 : 8;           // elements per 16 bytes: TMA needs 16-byte aligned rows
+  return (dtype == AFL_F32 || dtype == AFL_BF16) && (ld % per16 == 0) && (reinterpret_cast<uintptr_t>(G) % 16 == 0) && n >= 1 &&
+         d >= 1 && n <= 4096 && d < (int64_t(1) << 31) - 64;
 }
 
 static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, int flags) {
@@ -618,7 +619,9 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     pl.parts_bytes = static_cast<size_t>(pairs) * pl.splits * kPartElems * sizeof(float);
     // N > 128: the triangular bf16x2 tile-pair kernel (AFL_GRAM_TF32X2 / AFL_GRAM_KERNEL=tf32 keeps the round-1
     // all-ordered-pairs split-TF32 kernel for comparison)
-    pl.pair = n > kTileRows && !(flags & (AFL_GRAM_SINGLE_PASS | AFL_GRAM_TF32X2)) && !(kenv && kenv[0] == 't');
+    pl.pair = (n > kTileRows && !(flags & (AFL_GRAM_SINGLE_PASS | AFL_GRAM_TF32X2)) && !(kenv && kenv[0] == 't')) ||
+              dtype == AFL_BF16;      // bf16 matrices: TMA delivers ready-made operand tiles to the pair kernel (any n)
+    if (dtype == AFL_BF16) pl.bf16 = false;
     if (pl.pair) { pl.splits = pair_splits(n, d); pl.parts_bytes = pair_parts_bytes(n, d); }
     pl.s_bytes = align_up(2 * static_cast<size_t>(n) * n * sizeof(double), 256);
     pl.total = pl.parts_bytes + pl.s_bytes;
@@ -637,8 +640,8 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
 
 size_t workspace_bytes(int n, int64_t d, int dtype, int flags) {
   // Upper bound that holds for either path (the pointer alignment is unknown here).
-  Plan a = make_plan(reinterpret_cast<const void*>(16), n, d, 4, dtype, flags & ~AFL_GRAM_FORCE_SIMT);
-  Plan b = make_plan(reinterpret_cast<const void*>(16), n, d, 4, dtype, flags | AFL_GRAM_FORCE_SIMT);
+  Plan a = make_plan(reinterpret_cast<const void*>(16), n, d, 8, dtype, flags & ~AFL_GRAM_FORCE_SIMT);
+  Plan b = make_plan(reinterpret_cast<const void*>(16), n, d, 8, dtype, flags | AFL_GRAM_FORCE_SIMT);
   return (a.total > b.total ? a.total : b.total) + 256;
 }
 
@@ -671,7 +674,7 @@ int sqdist_partial_ex(const void* G, int n, int64_t d, int64_t ld, int dtype, do
     if (pl.pair) {
       float* parts = static_cast<float*>(ws);
       double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
-      return launch_pair(static_cast<const float*>(G), n, d, ld, parts, S, d2_out, pl.flush, center, stream);
+      return launch_pair(G, dtype, n, d, ld, parts, S, d2_out, pl.flush, center, stream);
     }
     if (pl.bf16) {
       float* parts = static_cast<float*>(ws);

@@ -53,6 +53,8 @@ struct PairParams {
   float* parts;         // [pairs][splits][2][128][128]
   const float* G;       // matrix base and pitch (elements): the J tile is loaded with cp.async (LDGSTS), not TMA
   int64_t ld;
+  int in_bf16;          // bf16 client matrix: TMA delivers ready-made SWIZZLE_128B operand tiles (b1 = g exactly, no b2,
+                        // no converter pass, no centring), one MMA per 16 columns
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_rn_p(float lo, float hi) {
@@ -142,7 +144,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
             const int b = i * nbx + t;
             const int s = slot_of(b);
             mbar_wait(&slot_free[s], phase_of(b) ^ 1u);
-            mbar_arrive_expect_tx(&raw_full[s], kPSlotBytes);
+            mbar_arrive_expect_tx(&raw_full[s], p.in_bf16 ? kPSlotBytes / 2 : kPSlotBytes);
             tma_load_2d(smem + static_cast<size_t>(s) * kPSlotBytes, &tmap, &raw_full[s], (split + i * p.splits) * kPCols,
                         (t == 0 ? ti : tj) * 128, pol);
           }
@@ -189,8 +191,13 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
         for (; it < it_end; it += 2) {
           const int s_i = slot_of(it * nbx);
           const int s_j = has_b ? slot_of(it * nbx + 1) : s_i;
-          named_bar_sync(1 + s_i, 32 + 32);              // the converter warp of that box has written and fenced it
-          if (has_b) named_bar_sync(1 + s_j, 32 + 32);
+          if (p.in_bf16) {                                // TMA wrote the operand tiles themselves
+            mbar_wait_fast(&raw_full[s_i], phase_of(it * nbx));
+            if (has_b) mbar_wait_fast(&raw_full[s_j], phase_of(it * nbx + 1));
+          } else {
+            named_bar_sync(1 + s_i, 32 + 32);            // the converter warp of that box has written and fenced it
+            if (has_b) named_bar_sync(1 + s_j, 32 + 32);
+          }
           // Strict alternation of the two issuers: k-block `it` is issued only after k-block it-1 has been, so every
           // CTA accumulates its k-blocks in the same order and identical rows get bit-identical sums in every tile
           // pair (and the table is reproducible run to run).  Barrier 8: issuer 0 -> 1, barrier 9: issuer 1 -> 0.
@@ -198,16 +205,19 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
           tc_fence_after();
           const uint32_t a_i = ring + static_cast<uint32_t>(s_i) * kPSlotBytes;
           const uint32_t a_j = ring + static_cast<uint32_t>(s_j) * kPSlotBytes;
-          const uint64_t d_b1i = umma_desc_sw128_sbo(a_i, 2048u), d_b2i = umma_desc_sw128_sbo(a_i + 1024u, 2048u);
-          const uint64_t d_b1j = umma_desc_sw128_sbo(a_j, 2048u), d_b2j = umma_desc_sw128_sbo(a_j + 1024u, 2048u);
+          const uint32_t sbo = p.in_bf16 ? 1024u : 2048u;
+          const uint64_t d_b1i = umma_desc_sw128_sbo(a_i, sbo), d_b2i = umma_desc_sw128_sbo(a_i + 1024u, 2048u);
+          const uint64_t d_b1j = umma_desc_sw128_sbo(a_j, sbo), d_b2j = umma_desc_sw128_sbo(a_j + 1024u, 2048u);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {             // 4 x K=16 bf16 = 64 columns; +32 bytes per step
               const uint64_t adv = static_cast<uint64_t>(ks * 2);
               const uint32_t acc = (it != it_begin) || (ks != 0);
               umma_bf16_p(d_hh, d_b1i + adv, d_b1j + adv, idesc, acc);       // hh += b1_I b1_J^T
-              umma_bf16_p(d_x, d_b1i + adv, d_b2j + adv, idesc, acc);        // X  += b1_I b2_J^T
-              umma_bf16_p(d_x, d_b2i + adv, d_b1j + adv, idesc, 1u);         // X  += b2_I b1_J^T
+              if (!p.in_bf16) {
+                umma_bf16_p(d_x, d_b1i + adv, d_b2j + adv, idesc, acc);      // X  += b1_I b2_J^T
+                umma_bf16_p(d_x, d_b2i + adv, d_b1j + adv, idesc, 1u);       // X  += b2_I b1_J^T
+              }
             }
             umma_commit(&slot_free[s_i]);
             if (has_b) umma_commit(&slot_free[s_j]);
@@ -242,7 +252,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
       return gram_center(p.cref, p.cref_rows, p.cref_ld, col, p.d);
     };
     cen = load_center(w4);
-    for (int box = w4; box < nboxes; box += 4) {
+    for (int box = w4; box < (p.in_bf16 ? 0 : nboxes); box += 4) {
       const int s = slot_of(box);
       const uint32_t ph = phase_of(box);
       const float4 cnext = load_center(box + 4);          // in flight while this box is converted
@@ -292,7 +302,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * 256 + a * 128);
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = 0; c < ((p.in_bf16 && a == 1) ? 0 : 8); c += 2) {
         uint32_t v0[16], v1[16];
         tmem_ld_32x32b_x16(taddr + c * 16, v0);
         tmem_ld_32x32b_x16(taddr + c * 16 + 16, v1);
@@ -383,9 +393,12 @@ size_t pair_parts_bytes(int n, int64_t d) {
   return static_cast<size_t>(pairs) * pair_splits(n, d) * kPPartElems * sizeof(float);
 }
 
-// G: fp32 [n, d], pitch ld (elements, multiple of 4), 16-byte aligned.  parts: pair_parts_bytes(); S: n*n doubles.
-int launch_pair(const float* G, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush,
+// G: fp32 [n, d] (pitch multiple of 4 elements) or bf16 (pitch multiple of 8), 16-byte aligned.
+// parts: pair_parts_bytes(); S: n*n doubles.
+int launch_pair(const void* Gv, int dtype, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush,
                 int center, cudaStream_t stream) {
+  const float* G = static_cast<const float*>(Gv);
+  const bool bf16 = dtype == AFL_BF16;
   static EncodeTiledFn3 enc = nullptr;
   if (!enc) {
     void* fp = nullptr;
@@ -399,7 +412,8 @@ int launch_pair(const float* G, int n, int64_t d, int64_t ld, float* parts, doub
   p.splits = pair_splits(n, d);
   p.kblocks = static_cast<int>((d + kPCols - 1) / kPCols);
   p.flush = flush < 2 ? 2 : (flush & ~1);
-  p.center = center ? 1 : 0;
+  p.center = (center && !bf16) ? 1 : 0;
+  p.in_bf16 = bf16 ? 1 : 0;
   p.cref_rows = n < kGramCenterRows ? n : kGramCenterRows;
   p.cref = G + static_cast<int64_t>(n - p.cref_rows) * ld;
   p.cref_ld = ld;
@@ -408,12 +422,12 @@ int launch_pair(const float* G, int n, int64_t d, int64_t ld, float* parts, doub
   p.G = G; p.ld = ld;
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * (bf16 ? 2 : 4)};
   const cuuint32_t box[2] = {kPCols, 128};
   const cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(G), gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(&tmap, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(Gv), gdim,
+                   gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", static_cast<int>(r)); return AFL_ERR_CUDA; }
   const size_t smem = static_cast<size_t>(kPSlots) * kPSlotBytes + 1024;
   static int smem_attr_done[kMaxDevices] = {0};

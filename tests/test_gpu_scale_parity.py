@@ -221,3 +221,33 @@ def test_two_devices_in_one_process(api):
             assert np.array_equal(D.krum(G, n, f), G[want])                     # host-buffer entry point on this device
             np.testing.assert_allclose(D.trimmed_mean(Gd[:, :2048].contiguous(), n, f).cpu().numpy(),
                                        co.trimmed_mean(G[:, :2048], f), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,d,f", [(100, 65536, 24), (300, 32768, 70), (1000, 16384, 240)])
+def test_bf16_clients_on_the_tensor_path(api, n, d, f):
+    """bf16 client matrices (north_star: "fp32 or bf16 tensors") reach the tcgen05 path: TMA delivers the operand tiles,
+    the products are exact, only the fp32 accumulation rounds.  Checker: float64 sums on the upcast values."""
+    D, _, dev, nat = api
+    rng = np.random.default_rng(81 + n)
+    Gd = torch.from_numpy(hetero(rng, n, d)).cuda().bfloat16()
+    G = Gd.float().cpu().numpy()
+    if n == 1000:
+        G[:f] = G[f]; Gd = torch.from_numpy(G).cuda().bfloat16()         # identical rows spanning two tiles
+    ref2 = co.pairwise_sqdist(G)
+    d2 = dev.sqdist_partial(Gd, nat.GRAM_FORCE_TCGEN05)
+    if n == 1000:
+        assert float(d2[:f + 1, :f + 1].abs().max()) == 0.0
+        sub = slice(f, None)
+        table_checks(d2.cpu().numpy()[sub, sub], ref2[sub, sub], 6e-6)
+    else:
+        table_checks(d2.cpu().numpy(), ref2, 6e-6)
+    want, margin = co.krum_select(np.sqrt(ref2), n, f, with_margin=True)
+    got = D.krum(Gd, n, f, return_index=True)
+    if margin > MARGIN or margin == 0.0:
+        assert got == want
+    if n >= 4 * f + 3:
+        out, sel = D.bulyan(Gd, n, f, return_selection=True)
+        gpu_table = D._krum_create_distances(Gd).dense.cpu().numpy().astype(np.float64)
+        assert sel.cpu().tolist() == co.bulyan_select(gpu_table, n, f)
+        np.testing.assert_allclose(out.cpu().numpy(), co.trimmed_mean(G, 2 * f, rows=sel.cpu().tolist()), rtol=1e-5,
+                                   atol=1e-6 * float(np.abs(G).mean()))
