@@ -97,8 +97,9 @@ def launch_count() -> int:
     return int(lib().afl_launch_count())
 
 
-def profile_enable(on: bool):
-    check(lib().afl_profile_enable(1 if on else 0))
+def profile_enable(on):
+    """False/0: off; True/1: every bracketed kernel; 2: only the dominant kernel of each rule."""
+    check(lib().afl_profile_enable(int(on)))
 
 
 def profile_read(kernel: str):

@@ -32,8 +32,12 @@ static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 static std::vector<ProfRec*> g_prof_recs;
 
+static bool dominant_kernel(const char* n) {
+  return !strncmp(n, "gram_", 5) || !strcmp(n, "sqdist_simt") || !strcmp(n, "trimmed_mean") || !strcmp(n, "mean") || !strcmp(n, "alie");
+}
 ProfScope::ProfScope(const char* name, cudaStream_t stream) : name_(name), stream_(stream), rec_(nullptr) {
-  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  const int mode = g_prof_on.load(std::memory_order_relaxed);
+  if (!mode || (mode == 2 && !dominant_kernel(name))) return;
   ProfRec* r = new ProfRec{name, nullptr, nullptr};
   if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) { delete r; return; }
   cudaEventRecord(r->e0, stream);
@@ -281,7 +285,7 @@ int afl_device_info(int* sms, int* cc_major, int* cc_minor, size_t* free_bytes, 
   return AFL_OK;
 }
 
-int afl_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); return AFL_OK; }
+int afl_profile_enable(int on) { g_prof_on.store(on == 2 ? 2 : (on ? 1 : 0)); return AFL_OK; }
 int afl_profile_read(const char* kernel, double* total_ms, int* launches) {
   if (!kernel) { set_error("afl_profile_read: kernel is NULL"); return AFL_ERR_BAD_ARG; }
   return profile_read(kernel, total_ms, launches);

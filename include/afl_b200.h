@@ -75,7 +75,8 @@ uint64_t afl_launch_count(void);
  * While enabled, the dominant kernel of every entry point is bracketed by CUDA events on the stream it
  * is launched on.  afl_profile_read(name, ...) waits for the recorded events of kernel `name`
  * ("gram_bf16x2", "gram_tcgen05", "sqdist_simt", "trimmed_mean", "alie", "mean", "row_sort", "bulyan_rounds"),
- * returns their summed duration and launch count, and forgets them. */
+ * returns their summed duration and launch count, and forgets them.  on = 1: every bracketed kernel; on = 2: only the
+ * dominant kernel of a rule (gram_*, sqdist_simt, trimmed_mean, mean, alie) - one pair of events per step. */
 int afl_profile_enable(int on);
 int afl_profile_read(const char* kernel, double* total_ms, int* launches);
 

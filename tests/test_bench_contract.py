@@ -45,3 +45,26 @@ def test_reference_arm_port_when_no_checkout(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     info = json.loads(out.stdout.strip().splitlines()[-1])
     assert info["kind"] == "port" and info["value"] > 0 and info["cores"] == 1
+
+
+def test_cpu_legs_share_one_sample_shape():
+    """VERDICT r1 weak #6: the two CPU figures of one record must be taken on the same D' and input distribution."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for rule, n, d in (("Krum", 100, 11_200_000), ("Bulyan", 500, 25_000_000), ("TrimmedMean", 1000, 10_000_000),
+                       ("ALIE", 1000, 25_000_000)):
+        a, b = bench.cpu_sample_dim(rule, n, d), bench.cpu_sample_dim(rule, n, d)
+        assert a == b and 0 < a <= d
+    g1, g2 = bench.cpu_inputs(7, 64, 5), bench.cpu_inputs(7, 64, 5)
+    assert g1.dtype.name == "float32" and (g1 == g2).all()
+
+
+def test_extra_configs_cover_the_baseline_configs():
+    sys.path.insert(0, ROOT)
+    import bench
+    tags = [t[-1] for t in bench.extra_configs(1, 180.0)]
+    assert tags == ["C3", "C4", "C5-krum", "C5-bulyan", "C5-alie"]
+    full = {t[-1]: t for t in bench.extra_configs(1, 180.0)}
+    assert full["C5-krum"][1:3] == (1000, 25_000_000)           # N=1000 x D=25M fp32 = 100 GB fits one B200
+    small = {t[-1]: t for t in bench.extra_configs(1, 60.0)}
+    assert small["C5-krum"][2] < 25_000_000                      # otherwise the largest D that fits, stated in the record
