@@ -521,8 +521,9 @@ int launch_bf16x2(const float* G, int n, int64_t d, int64_t ld, float* parts, in
 // tile-pair bf16x2 kernel for N > 128 (gram_pair.cu)
 int pair_splits(int n, int64_t d);
 size_t pair_parts_bytes(int n, int64_t d);
-int launch_pair(const void* G, int dtype, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush,
-                int center, cudaStream_t stream);
+size_t pair_center_bytes(int64_t d);
+int launch_pair(const void* G, int dtype, int n, int64_t d, int64_t ld, float* parts, double* S, float* cvec, double* d2_out,
+                int flush, int center, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -624,7 +625,7 @@ static Plan make_plan(const void* G, int n, int64_t d, int64_t ld, int dtype, in
     if (dtype == AFL_BF16) pl.bf16 = false;
     if (pl.pair) { pl.splits = pair_splits(n, d); pl.parts_bytes = pair_parts_bytes(n, d); }
     pl.s_bytes = align_up(2 * static_cast<size_t>(n) * n * sizeof(double), 256);
-    pl.total = pl.parts_bytes + pl.s_bytes;
+    pl.total = pl.parts_bytes + pl.s_bytes + (pl.pair ? pair_center_bytes(d) : 0);
   } else {
     const int t32 = (n + 31) / 32;
     int64_t chunks = (d + 31) / 32;
@@ -674,7 +675,8 @@ int sqdist_partial_ex(const void* G, int n, int64_t d, int64_t ld, int dtype, do
     if (pl.pair) {
       float* parts = static_cast<float*>(ws);
       double* S = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + pl.parts_bytes);
-      return launch_pair(G, dtype, n, d, ld, parts, S, d2_out, pl.flush, center, stream);
+      float* cvec = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + pl.parts_bytes + pl.s_bytes);
+      return launch_pair(G, dtype, n, d, ld, parts, S, cvec, d2_out, pl.flush, center, stream);
     }
     if (pl.bf16) {
       float* parts = static_cast<float*>(ws);

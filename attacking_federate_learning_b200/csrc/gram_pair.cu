@@ -49,6 +49,7 @@ struct PairParams {
   int center;           // subtract the last client's row while converting
   const float* cref;    // first of the last cref_rows rows
   int cref_rows; int64_t cref_ld;
+  const float* cvec;    // precomputed centre (mean of those rows), padded with zeros to a multiple of 64 columns
   int64_t d;
   float* parts;         // [pairs][splits][2][128][128]
   const float* G;       // matrix base and pitch (elements): the J tile is loaded with cp.async (LDGSTS), not TMA
@@ -249,7 +250,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p) {
     auto load_center = [&](int box) -> float4 {
       if (!(p.center && box < nboxes)) return make_float4(0.f, 0.f, 0.f, 0.f);
       const int64_t col = static_cast<int64_t>(split + (box / nbx) * p.splits) * kPCols + c16 * 4;
-      return gram_center(p.cref, p.cref_rows, p.cref_ld, col, p.d);
+      return __ldg(reinterpret_cast<const float4*>(p.cvec + col));     // one load per box (measured: 8 row loads cost 12 %)
     };
     cen = load_center(w4);
     for (int box = w4; box < (p.in_bf16 ? 0 : nboxes); box += 4) {
@@ -376,6 +377,15 @@ __global__ void pair_to_sqdist_kernel(const double* __restrict__ S, int n, doubl
   d2[static_cast<size_t>(i) * n + j] = v;
 }
 
+// centre vector: mean of the last `rows` clients, zero past d (the k-blocks are 64 columns wide)
+__global__ void __launch_bounds__(256)
+pair_center_kernel(const float* __restrict__ cref, int rows, int64_t ld, int64_t d, int64_t d_pad, float* __restrict__ cvec) {
+  const int64_t col = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (col >= d_pad) return;
+  const float4 c = gram_center(cref, rows, ld, col, d);
+  *reinterpret_cast<float4*>(cvec + col) = c;
+}
+
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -388,6 +398,7 @@ int pair_splits(int n, int64_t d) {
   if (s > kblocks) s = static_cast<int>(kblocks);
   return s < 1 ? 1 : s;
 }
+size_t pair_center_bytes(int64_t d) { return align_up(static_cast<size_t>((d + kPCols - 1) / kPCols * kPCols) * sizeof(float), 256); }
 size_t pair_parts_bytes(int n, int64_t d) {
   const int tiles = (n + 127) / 128, pairs = tiles * (tiles + 1) / 2;
   return static_cast<size_t>(pairs) * pair_splits(n, d) * kPPartElems * sizeof(float);
@@ -395,8 +406,8 @@ size_t pair_parts_bytes(int n, int64_t d) {
 
 // G: fp32 [n, d] (pitch multiple of 4 elements) or bf16 (pitch multiple of 8), 16-byte aligned.
 // parts: pair_parts_bytes(); S: n*n doubles.
-int launch_pair(const void* Gv, int dtype, int n, int64_t d, int64_t ld, float* parts, double* S, double* d2_out, int flush,
-                int center, cudaStream_t stream) {
+int launch_pair(const void* Gv, int dtype, int n, int64_t d, int64_t ld, float* parts, double* S, float* cvec, double* d2_out,
+                int flush, int center, cudaStream_t stream) {
   const float* G = static_cast<const float*>(Gv);
   const bool bf16 = dtype == AFL_BF16;
   static EncodeTiledFn3 enc = nullptr;
@@ -420,6 +431,12 @@ int launch_pair(const void* Gv, int dtype, int n, int64_t d, int64_t ld, float* 
   p.d = d;
   p.parts = parts;
   p.G = G; p.ld = ld;
+  p.cvec = cvec;
+  if (p.center) {
+    const int64_t d_pad = (d + kPCols - 1) / kPCols * kPCols;
+    pair_center_kernel<<<static_cast<unsigned>((d_pad / 4 + 255) / 256), 256, 0, stream>>>(p.cref, p.cref_rows, ld, d, d_pad, cvec);
+    AFL_LAUNCH_CHECK("pair_center_kernel");
+  }
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * (bf16 ? 2 : 4)};

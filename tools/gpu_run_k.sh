@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_scale_parity.py tests/test_gpu_parity.py -m gpu -q --timeout 300 -p no:cacheprovider -k "gram or krum or bulyan or alie or bf16_clients or identical" > gpurun_out/r02_k_pytest.txt 2>&1
+B="--extras off --no-cpu-baseline --e2e-steps 0"
+timeout 300 python bench.py --rule Bulyan --clients 500 --dim 2500000 --byzantine 100 --steps 5 $B > gpurun_out/r02_k_bulyan500.json 2> gpurun_out/r02_k_bulyan500.err
+timeout 300 python bench.py --rule Krum --clients 1000 --dim 524288 --steps 5 $B > gpurun_out/r02_k_krum1000_524k.json 2> gpurun_out/r02_k_krum1000_524k.err
+timeout 300 python bench.py --rule Krum --clients 1000 --dim 3125000 --steps 5 $B > gpurun_out/r02_k_krum1000_3m.json 2> gpurun_out/r02_k_krum1000_3m.err
+tail -3 gpurun_out/r02_k_pytest.txt
