@@ -483,8 +483,10 @@ __device__ __noinline__ float general_column(const Params& P, const uint32_t* ti
 
 constexpr int kScratchWords = 320;             // per warp: candidate lists [8][32] words + two dense u16[64] arrays
 
+// S <= 16 (up to 512 rows: Bulyan's second stage at N = 500) leaves room for four CTAs per SM in shared memory; ask
+// the compiler for 64 registers there (the kernel is latency-bound: resident warps are what it needs)
 template <int S, bool BF16>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, (S <= 16 ? 4 : 3))
 trimmed_mean_kernel(const Params P) {
   extern __shared__ __align__(1024) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots] + scratch
   constexpr int kGroups = S / 4;
