@@ -41,7 +41,8 @@ def table_checks(d2, ref2, bias_cap, spread_cap=3e-6):
     assert np.array_equal(d2, d2.T) and not d2.diagonal().any()
 
 
-@pytest.mark.parametrize("n,d,seed", [(500, 65536, 11), (1000, 65536, 12), (257, 32768, 13), (640, 16384 + 64, 14)])
+@pytest.mark.parametrize("n,d,seed", [(500, 65536, 11), (1000, 65536, 12), (257, 32768, 13), (640, 16384 + 64, 14),
+                                      (300, 4100, 15), (129, 20004, 16)])     # ragged last k-block (d % 64 != 0)
 def test_gram_tile_pairs_vs_float64(api, n, d, seed):
     """N > 128: the tile-pair tcgen05 path (aligned pitch) against float64 sums of fl32 differences."""
     _, _, dev, nat = api
@@ -223,7 +224,7 @@ def test_two_devices_in_one_process(api):
                                        co.trimmed_mean(G[:, :2048], f), rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("n,d,f", [(100, 65536, 24), (300, 32768, 70), (1000, 16384, 240)])
+@pytest.mark.parametrize("n,d,f", [(100, 65536, 24), (300, 32768, 70), (1000, 16384, 240), (150, 8200, 30)])
 def test_bf16_clients_on_the_tensor_path(api, n, d, f):
     """bf16 client matrices (north_star: "fp32 or bf16 tensors") reach the tcgen05 path: TMA delivers the operand tiles,
     the products are exact, only the fp32 accumulation rounds.  Checker: float64 sums on the upcast values."""
