@@ -207,6 +207,7 @@ __device__ __forceinline__ float tie_sum(const float (&v)[S], float T, int need,
     unsigned bm[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) bm[q] = __ballot_sync(0xffffffffu, fabsf(v[g + q]) == T);
+    if ((bm[0] | bm[1] | bm[2] | bm[3]) == 0u) continue;       // no member of the tie group in these 128 rows (warp-uniform)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {           // true slot order inside the group
       const int q = kk ^ jx;
@@ -220,6 +221,28 @@ __device__ __forceinline__ float tie_sum(const float (&v)[S], float T, int need,
     }
   }
   return part;
+}
+
+// Ascending 32-lane bitonic sort of one float per lane by keyof<KEYS>() (|v| for KEYS); lanes with equal keys keep
+// their own value, so nothing is duplicated or lost.
+template <bool KEYS>
+__device__ __forceinline__ float warp_sort32(float v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float p = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = (k == 32) ? true : ((lane & k) == 0);
+      const bool take_min = ((lane & j) == 0) == up;
+      if (KEYS) {
+        const float av = fabsf(v), ap = fabsf(p);
+        v = take_min ? (ap < av ? p : v) : (ap > av ? p : v);
+      } else {
+        v = take_min ? fminf(v, p) : fmaxf(v, p);
+      }
+    }
+  }
+  return v;
 }
 
 constexpr int kCap = 4;                       // lane-local candidate list capacity (fast path)
@@ -289,30 +312,24 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
       __syncwarp();
       const bool have = lane < cin;
       const float val = have ? dense[lane] : kInf;
-      const float key = have ? keyof<KEYS>(val) : kInf;
-      // rank in the strict order (key, lane): all ranks distinct; 31 shuffles, 3 ALU ops per step
-      int rank = 0;
-#pragma unroll
-      for (int t = 1; t < 32; ++t) {
-        const float ok = __shfl_sync(0xffffffffu, key, (lane + t) & 31);
-        const bool wrapped = lane >= 32 - t;              // source lane (lane + t) & 31 is below this lane
-        rank += ((ok < key) || (wrapped && ok == key)) ? 1 : 0;
-      }
+      // 15-stage shuffle bitonic sort of the (<= 32) candidates by key; equal keys may end up in any order, which
+      // is fine: for the median equal keys are equal values, for the |dev| threshold a tie group that the keep
+      // boundary cuts is resolved in row order by tie_sum() on the register-resident column, not on these lanes.
+      // (round 1 ranked every candidate against every other: 31 shuffles + 93 ALU ops, 21 % of the kernel.)
+      const float sv = warp_sort32<KEYS>(val, lane);
       if (!KEYS) {
-        const unsigned ma = __ballot_sync(0xffffffffu, rank == r1 - c_a);
-        const unsigned mb = __ballot_sync(0xffffffffu, rank == r2 - c_a);
-        out_a = __shfl_sync(0xffffffffu, val, __ffs(ma) - 1);
-        out_b = __shfl_sync(0xffffffffu, val, __ffs(mb) - 1);
+        out_a = __shfl_sync(0xffffffffu, sv, r1 - c_a);
+        out_b = __shfl_sync(0xffffffffu, sv, r2 - c_a);
         return true;
       }
+      const float skey = fabsf(sv);
       const int take = r1 + 1 - c_a;            // number of candidates kept, in (key, row) order
-      const unsigned mt = __ballot_sync(0xffffffffu, rank == take - 1);          // the boundary candidate
-      const float T = __shfl_sync(0xffffffffu, key, __ffs(mt) - 1);
-      const int n_less = __popc(__ballot_sync(0xffffffffu, have && key < T));
-      const int group = __popc(__ballot_sync(0xffffffffu, have && key == T));
+      const float T = __shfl_sync(0xffffffffu, skey, take - 1);                  // the boundary candidate's key
+      const int n_less = __popc(__ballot_sync(0xffffffffu, have && skey < T));
+      const int group = __popc(__ballot_sync(0xffffffffu, have && skey == T));
       const int need = take - n_less;
-      float part = sa + ((have && key < T) ? val : 0.f);
-      if (need == group) part += (have && key == T) ? val : 0.f;     // whole tie group kept: order irrelevant
+      float part = sa + ((have && skey < T) ? sv : 0.f);
+      if (need == group) part += (have && skey == T) ? sv : 0.f;    // whole tie group kept: order irrelevant
       else part += tie_sum<S>(v, T, need, jx, lane);                   // boundary cuts the group: row order
       out_a = warp_sum(part);
       return true;
