@@ -245,23 +245,60 @@ __device__ __forceinline__ float warp_sort32(float v, int lane) {
   return v;
 }
 
-constexpr int kCap = 4;                       // lane-local candidate list capacity (fast path)
+// Where a register-resident column lives in the shared-memory tile, so that a candidate can be re-read by a
+// run-time register index (a dynamic index into the register array itself would spill it to local memory).
+struct ColRef {
+  const uint32_t* words;     // tile word of element 0 for this lane; element i is words[(i >> 2) * 128 + (i & 3)]
+  int half;                  // bf16: which half of the word
+  float med;                 // KEYS: the median that was subtracted from the registers
+};
+template <bool BF16, bool KEYS>
+__device__ __forceinline__ float col_fetch(const ColRef& c, int i) {
+  const uint32_t w = c.words[(i >> 2) * 128 + (i & 3)];
+  const float x = BF16 ? __uint_as_float(c.half ? (w & 0xFFFF0000u) : (w << 16)) : __uint_as_float(w);
+  return KEYS ? __fsub_rn(x, c.med) : x;
+}
+
+// One element of the fused pass: below = key < a; ca += below; (KEYS) sa += below ? v : 0; inmask |= bit when
+// a <= key < b.  Written in PTX so that it stays 4 (5) instructions: the C++ form was compiled to 14 per element
+// (the count became a set/clear bit mask, and the list address was rebuilt under every store's predicate).
+template <bool KEYS>
+__device__ __forceinline__ void fused_step(float v, float a, float b, uint32_t bit, int& ca, uint32_t& inmask, float& sa) {
+  if (KEYS) {
+    asm("{\n\t.reg .pred p, q;\n\t.reg .f32 k;\n\t"
+        "abs.f32 k, %3;\n\t"
+        "setp.lt.f32 p, k, %4;\n\t"
+        "setp.lt.and.f32 q, k, %5, !p;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t"
+        "@p add.rn.f32 %2, %2, %3;\n\t"
+        "@q or.b32 %1, %1, %6;\n\t}"
+        : "+r"(ca), "+r"(inmask), "+f"(sa)
+        : "f"(v), "f"(a), "f"(b), "r"(bit));
+  } else {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f32 p, %2, %3;\n\t"
+        "setp.lt.and.f32 q, %2, %4, !p;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t"
+        "@q or.b32 %1, %1, %5;\n\t}"
+        : "+r"(ca), "+r"(inmask)
+        : "f"(v), "f"(a), "f"(b), "r"(bit));
+  }
+}
 
 // Fast path.  One fused pass over the registers with a model bracket [a, b): counts #{key < a} (and the
-// lane-local dev sum below a), and appends in-bracket elements to a lane-local list in shared memory
-// with predicated stores only (no ballots, no branches; the list wraps instead of overflowing and the
-// wrap is detected from the count).  If the target rank(s) fall inside and <= 32 candidates were
-// collected, they are compacted to one per lane and ranked with 31 shuffles.  Returns false (state
-// updated: lo/c_lo/sum_lo or hi/c_hi tightened where the pass proved a bound) when the general path
-// has to take over.
-template <int S, bool KEYS>
-__device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, int r2, float p0, float density,
-                                            int lane, int jx, uint32_t* scratch, float& lo, float& hi, int& c_lo,
-                                            int& c_hi, float& sum_lo, float& out_a, float& out_b) {
+// lane-local dev sum below a) and marks the in-bracket elements in a per-lane bit mask (no stores, no ballots,
+// no branches).  If the target rank(s) fall inside and <= 32 candidates were marked, each lane re-reads its
+// few candidates from the tile into a dense 32-entry list (exclusive prefix of the per-lane counts), and the
+// list is sorted with a 15-stage shuffle network.  Returns false (state updated: lo/c_lo/sum_lo or hi/c_hi
+// tightened where the pass proved a bound) when the general path has to take over.
+template <int S, bool KEYS, bool BF16>
+__device__ __forceinline__ bool select_fast(const float (&v)[S], const ColRef& col, int n, int r1, int r2, float p0,
+                                            float density, int lane, int jx, uint32_t* scratch, float& lo, float& hi,
+                                            int& c_lo, int& c_hi, float& sum_lo, float& out_a, float& out_b) {
+  static_assert(S <= 32, "one mask bit per register-resident element");
   if (!((density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf))) return false;
   float center = p0;
   float halfw = (11.f + 0.5f * static_cast<float>(r2 - r1)) / density;
-  const uint32_t list_base = smem_u32(scratch) + lane * 4;       // lists: [kCap][32] words
 #pragma unroll 1
   for (int attempt = 0; attempt < 3; ++attempt) {
     float a = center - halfw, b = center + halfw;
@@ -271,27 +308,15 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
     if (!(a < b)) return false;
     int ca = 0;
     float sa = 0.f;
-    uint32_t off = 0;
+    uint32_t inmask = 0u;
 #pragma unroll
-    for (int i = 0; i < S; ++i) {
-      const float k = keyof<KEYS>(v[i]);
-      const bool below = k < a;
-      ca += below ? 1 : 0;
-      if (KEYS) sa += below ? v[i] : 0.f;
-      const bool in = !below && (k < b);
-      const uint32_t addr = list_base + (off & ((kCap - 1) * 128u));   // wraps instead of overflowing
-      if (in) {
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(__float_as_uint(v[i])) : "memory");
-        off += 128u;
-      }
-    }
-    const int mine = static_cast<int>(off >> 7);
+    for (int i = 0; i < S; ++i) fused_step<KEYS>(v[i], a, b, 1u << i, ca, inmask, sa);
+    const int mine = __popc(inmask);
     const int c_a = warp_sum_i(ca);
     const int cin = warp_sum_i(mine);
-    const int cmax = __reduce_max_sync(0xffffffffu, mine);
     const int c_b = c_a + cin;
     const bool inside = (c_a <= r1) && (r2 < c_b);
-    if (inside && cin <= 32 && cmax <= kCap) {
+    if (inside && cin <= 32) {
       // ---- dense compaction: exclusive prefix of the per-lane counts, then one candidate per lane
       int incl = mine;
 #pragma unroll
@@ -299,19 +324,13 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], int n, int r1, 
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      const int excl = incl - mine;
-      __syncwarp();
-      float ent[kCap];
-#pragma unroll
-      for (int k = 0; k < kCap; ++k) ent[k] = __uint_as_float(scratch[k * 32 + lane]);
-      __syncwarp();
-      float* dense = reinterpret_cast<float*>(scratch) + kCap * 32;   // [32] after the lists
-#pragma unroll
-      for (int k = 0; k < kCap; ++k)
-        if (k < mine) dense[excl + k] = ent[k];
+      float* dense = reinterpret_cast<float*>(scratch);              // [32]
+      int pos = incl - mine;
+      for (uint32_t m = inmask; m != 0u; m &= m - 1u) dense[pos++] = col_fetch<BF16, KEYS>(col, __ffs(m) - 1);
       __syncwarp();
       const bool have = lane < cin;
       const float val = have ? dense[lane] : kInf;
+      __syncwarp();
       // 15-stage shuffle bitonic sort of the (<= 32) candidates by key; equal keys may end up in any order, which
       // is fine: for the median equal keys are equal values, for the |dev| threshold a tie group that the keep
       // boundary cuts is resolved in row order by tie_sum() on the register-resident column, not on these lanes.
@@ -438,6 +457,7 @@ __device__ __noinline__ float general_column(const Params& P, const uint32_t* ti
   const float fn = static_cast<float>(n);
   const int jx = (cw >> 2) & 3;
   const uint4* t4 = reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane;
+  ColRef col{reinterpret_cast<const uint32_t*>(t4), half, 0.f};
   float x[S];
 #pragma unroll
   for (int m = 0; m < kGroups; ++m) {
@@ -473,7 +493,7 @@ __device__ __noinline__ float general_column(const Params& P, const uint32_t* ti
   {
     float lo = -kInf, hi = kInf, sl = 0.f;
     int c_lo = 0, c_hi = n;
-    if (!select_fast<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
+    if (!select_fast<S, false, BF16>(x, col, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
                                c_hi, sl, a, b))
       warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
                             c_hi, 0.f, a, b);
@@ -489,7 +509,8 @@ __device__ __noinline__ float general_column(const Params& P, const uint32_t* ti
     float total, unused;
     float lo = -kInf, hi = kInf, sl = 0.f;
     int c_lo = 0, c_hi = n;
-    if (!select_fast<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
+    col.med = med;
+    if (!select_fast<S, true, BF16>(x, col, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
                               c_lo, c_hi, sl, total, unused))
       warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
                            c_lo, c_hi, sl, total, unused);
