@@ -249,13 +249,13 @@ __device__ __forceinline__ float warp_sort32(float v, int lane) {
 // run-time register index (a dynamic index into the register array itself would spill it to local memory).
 struct ColRef {
   const uint32_t* words;     // tile word of element 0 for this lane; element i is words[(i >> 2) * 128 + (i & 3)]
-  int half;                  // bf16: which half of the word
+  uint32_t unpack_sel;       // bf16: PRMT selector that moves the column's half of the word to the top (0x1044 / 0x3244)
   float med;                 // KEYS: the median that was subtracted from the registers
 };
 template <bool BF16, bool KEYS>
 __device__ __forceinline__ float col_fetch(const ColRef& c, int i) {
   const uint32_t w = c.words[(i >> 2) * 128 + (i & 3)];
-  const float x = BF16 ? __uint_as_float(c.half ? (w & 0xFFFF0000u) : (w << 16)) : __uint_as_float(w);
+  const float x = BF16 ? __uint_as_float(__byte_perm(w, 0u, c.unpack_sel)) : __uint_as_float(w);
   return KEYS ? __fsub_rn(x, c.med) : x;
 }
 
@@ -298,7 +298,8 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], const ColRef& c
   static_assert(S <= 32, "one mask bit per register-resident element");
   if (!((density > 0.f) && (density < kInf) && (p0 == p0) && (fabsf(p0) < kInf))) return false;
   float center = p0;
-  float halfw = (11.f + 0.5f * static_cast<float>(r2 - r1)) / density;
+  const float inv_density = __fdividef(1.f, density);       // model only: approximate division is enough
+  float halfw = (11.f + 0.5f * static_cast<float>(r2 - r1)) * inv_density;
 #pragma unroll 1
   for (int attempt = 0; attempt < 3; ++attempt) {
     float a = center - halfw, b = center + halfw;
@@ -370,15 +371,15 @@ __device__ __forceinline__ bool select_fast(const float (&v)[S], const ColRef& c
     if (c_a <= r1) { lo = a; c_lo = c_a; sum_lo = sa; } else { hi = a; c_hi = c_a; }
     if (c_b > r2 && b < hi) { hi = b; c_hi = c_b; }
     if (inside) {                                   // too many candidates: shrink around the interpolated rank
-      const float w = (b - a) / static_cast<float>(cin > 0 ? cin : 1);
+      const float w = __fdividef(b - a, static_cast<float>(cin > 0 ? cin : 1));
       center = a + (mid - static_cast<float>(c_a)) * w;
       halfw = 9.f * w;
     } else if (c_a > r2) {                          // target below the bracket
-      center = a - (static_cast<float>(c_a) - mid) / density;
-      halfw = (5.f + 0.35f * (static_cast<float>(c_a) - mid)) / density;
+      center = a - (static_cast<float>(c_a) - mid) * inv_density;
+      halfw = (5.f + 0.35f * (static_cast<float>(c_a) - mid)) * inv_density;
     } else {                                        // target above the bracket
-      center = b + (mid - static_cast<float>(c_b)) / density;
-      halfw = (5.f + 0.35f * (mid - static_cast<float>(c_b))) / density;
+      center = b + (mid - static_cast<float>(c_b)) * inv_density;
+      halfw = (5.f + 0.35f * (mid - static_cast<float>(c_b))) * inv_density;
     }
   }
   return false;
@@ -397,67 +398,88 @@ __device__ __forceinline__ void stage_tile(const Params& P, uint32_t* tile, int6
   const uint32_t sentinel = BF16 ? 0x7F807F80u : 0x7F800000u;
   const uint8_t* base = static_cast<const uint8_t*>(P.G);
   constexpr int kIters = (32 * S * 4) / kThreads;      // S/2
-  constexpr int kBatch = kIters < 4 ? kIters : 4;
   const bool full_tile = P.vec_ok && (col0 + cols_per_tile <= P.d);
   const int rowq = tid >> 2, j = tid & 3, l = rowq & 31, hi2 = tid >> 7;
   uint32_t* b0 = tile + (4 * j * kGroups) * 128 + l * 4 + (hi2 ^ j);
   uint32_t* b1 = tile + (4 * j * kGroups) * 128 + l * 4 + ((2 + hi2) ^ j);
   const int64_t c = col0 + static_cast<int64_t>(j) * (16 / es);
+  if (full_tile) {
+    // every 16-byte load of the tile is issued before the first store: one DRAM round trip per CTA instead of
+    // one per batch of four (the kernel has the registers: the per-column code needs 80 anyway), and ~8
+    // instructions per load so that the whole path stays a few hundred bytes of code
+    // (branch-free: rows past n_rows re-read the last row and are replaced by the sentinel at the store)
+    int gr[kIters];
+    const int last = P.n_rows - 1;
+    if (P.row_index) {
 #pragma unroll
-  for (int it0 = 0; it0 < kIters; it0 += kBatch) {
-    uint4 val[kBatch];
+      for (int it = 0; it < kIters; ++it) gr[it] = P.row_index[min(it * 64 + rowq, last)];
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int r = (it0 + u) * 64 + rowq;
-      uint4 t = make_uint4(sentinel, sentinel, sentinel, sentinel);
-      if (r < P.n_rows) {
-        int gr = P.row_index ? P.row_index[r] : r;
-        gr = gr < 0 ? gr + P.n_total : gr;
-        const uint8_t* src = base + (static_cast<int64_t>(gr) * P.ld + c) * es;
-        if (full_tile) {
-          t = ldg_stream_u4(reinterpret_cast<const uint4*>(src));
-        } else {
-          uint32_t w[4] = {0u, 0u, 0u, 0u};
-          if (BF16) {
-            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+      for (int it = 0; it < kIters; ++it) gr[it] = gr[it] < 0 ? gr[it] + P.n_total : gr[it];
+    } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (c + e < P.d) w[e >> 1] |= static_cast<uint32_t>(s16[e]) << ((e & 1) * 16);
-          } else {
-            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (c + e < P.d) w[e] = s32[e];
-          }
-          t = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-      val[u] = t;
+      for (int it = 0; it < kIters; ++it) gr[it] = min(it * 64 + rowq, last);
     }
+    const uint8_t* colbase = base + c * es;
+    const int64_t row_bytes = P.ld * es;
+    uint4 val[kIters];
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const int it = it0 + u;
+    for (int it = 0; it < kIters; ++it)
+      val[it] = ldg_stream_u4(reinterpret_cast<const uint4*>(colbase + gr[it] * row_bytes));
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const bool pad = it * 64 + rowq > last;
       uint32_t* b = (it & 1) ? b1 : b0;
       const int m = it >> 1;
-      b[(0 * kGroups + m) * 128] = val[u].x;
-      b[(1 * kGroups + m) * 128] = val[u].y;
-      b[(2 * kGroups + m) * 128] = val[u].z;
-      b[(3 * kGroups + m) * 128] = val[u].w;
+      b[(0 * kGroups + m) * 128] = pad ? sentinel : val[it].x;
+      b[(1 * kGroups + m) * 128] = pad ? sentinel : val[it].y;
+      b[(2 * kGroups + m) * 128] = pad ? sentinel : val[it].z;
+      b[(3 * kGroups + m) * 128] = pad ? sentinel : val[it].w;
     }
+    return;
+  }
+  // ragged last tile / unaligned matrix: element-wise, one rolled iteration at a time (cold: keep the code small)
+#pragma unroll 1
+  for (int it = 0; it < kIters; ++it) {
+    const int r = it * 64 + rowq;
+    uint32_t w[4] = {sentinel, sentinel, sentinel, sentinel};
+    if (r < P.n_rows) {
+      int gr = P.row_index ? P.row_index[r] : r;
+      gr = gr < 0 ? gr + P.n_total : gr;
+      const uint8_t* src = base + (static_cast<int64_t>(gr) * P.ld + c) * es;
+      w[0] = w[1] = w[2] = w[3] = 0u;
+      if (BF16) {
+        const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c + e < P.d) w[e >> 1] |= static_cast<uint32_t>(s16[e]) << ((e & 1) * 16);
+      } else {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < P.d) w[e] = s32[e];
+      }
+    }
+    uint32_t* b = ((it & 1) ? b1 : b0) + (it >> 1) * 128;
+    b[(0 * kGroups) * 128] = w[0];
+    b[(1 * kGroups) * 128] = w[1];
+    b[(2 * kGroups) * 128] = w[2];
+    b[(3 * kGroups) * 128] = w[3];
   }
 }
 
 // ---------------- general per-column path (any data): one warp, one column ----------------
 // `half` selects the bf16 column inside the 32-bit word-column cw (ignored for fp32).
 template <int S, bool BF16>
-__device__ __noinline__ float general_column(const Params& P, const uint32_t* tile, int cw, int half, uint32_t* scratch,
-                                             int lane) {
+__device__ __forceinline__ float general_column_impl(const Params& P, const uint32_t* tile, int cw, int half,
+                                                     uint32_t* scratch, int lane) {
   constexpr int kGroups = S / 4;
   const int n = P.n_rows;
   const float fn = static_cast<float>(n);
   const int jx = (cw >> 2) & 3;
   const uint4* t4 = reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane;
-  ColRef col{reinterpret_cast<const uint32_t*>(t4), half, 0.f};
+  // bf16 -> fp32 is one PRMT with a run-time selector (`half` is a loop variable: a ?: costs two predicated instructions)
+  const uint32_t unpack_sel = half ? 0x3244u : 0x1044u;
+  ColRef col{reinterpret_cast<const uint32_t*>(t4), unpack_sel, 0.f};
   float x[S];
 #pragma unroll
   for (int m = 0; m < kGroups; ++m) {
@@ -465,37 +487,40 @@ __device__ __noinline__ float general_column(const Params& P, const uint32_t* ti
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      x[4 * m + q] = BF16 ? __uint_as_float(half ? (w[q] & 0xFFFF0000u) : (w[q] << 16)) : __uint_as_float(w[q]);
+      x[4 * m + q] = BF16 ? __uint_as_float(__byte_perm(w[q], 0u, unpack_sel)) : __uint_as_float(w[q]);
   }
 
-  // mean / sigma of the column (pivot model only; never enters the result)
+  // mean / sigma of the column (pivot model only; never enters the result).  The kernel is instantiated with
+  // 16 * S < n_rows <= 32 * S (S >= 8), so the first half of the slot groups holds real rows only; in the second half a
+  // padded row is +inf and is skipped by predicate (no branches: the warp-uniform "is this group full" tests of
+  // round 1 cost an instruction-fetch bubble each).
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int m = 0; m < kGroups; ++m) {
-    if ((4 * m + 4) * 32 <= n) {                    // every row of this slot group exists (warp-uniform)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { s1 += x[4 * m + q]; s2 = fmaf(x[4 * m + q], x[4 * m + q], s2); }
+  for (int i = 0; i < S; ++i) {
+    if (S >= 8 && i < S / 2) {             // the launcher picks S with 16 * S < n_rows for S >= 8
+      s1 += x[i]; s2 = fmaf(x[i], x[i], s2);
     } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float t = (x[4 * m + q] < kInf) ? x[4 * m + q] : 0.f;   // padded rows are +inf
-        s1 += t; s2 = fmaf(t, t, s2);
-      }
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.lt.f32 p, %2, 0f7F800000;\n\t"
+          "@p add.rn.f32 %0, %0, %2;\n\t"
+          "@p fma.rn.f32 %1, %2, %2, %1;\n\t}"
+          : "+f"(s1), "+f"(s2) : "f"(x[i]));
     }
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
-  const float mean = s1 / fn;
-  const float var = fmaxf(s2 / fn - mean * mean, 0.f);
-  const float sd = sqrtf(var);
+  const float mean = __fdividef(s1, fn);
+  const float var = fmaxf(__fdividef(s2, fn) - mean * mean, 0.f);
+  const float inv_sd = rsqrtf(var);              // var == 0: +inf -> the densities below fail the model test
+  const float sd = var * inv_sd;                 // (NaN for var == 0: same effect on the |dev| pivot)
 
   // median (np.median: even N -> mean of the two middle order statistics, fp32)
   float a, b;
   {
     float lo = -kInf, hi = kInf, sl = 0.f;
     int c_lo = 0, c_hi = n;
-    if (!select_fast<S, false, BF16>(x, col, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
+    if (!select_fast<S, false, BF16>(x, col, n, (n - 1) >> 1, n >> 1, mean, P.med_density * inv_sd, lane, jx, scratch, lo, hi, c_lo,
                                c_hi, sl, a, b))
-      warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density / sd, lane, jx, scratch, lo, hi, c_lo,
+      warp_select<S, false>(x, n, (n - 1) >> 1, n >> 1, mean, P.med_density * inv_sd, lane, jx, scratch, lo, hi, c_lo,
                             c_hi, 0.f, a, b);
   }
   const float med = ((n & 1) != 0) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
@@ -510,13 +535,20 @@ __device__ __noinline__ float general_column(const Params& P, const uint32_t* ti
     float lo = -kInf, hi = kInf, sl = 0.f;
     int c_lo = 0, c_hi = n;
     col.med = med;
-    if (!select_fast<S, true, BF16>(x, col, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
+    if (!select_fast<S, true, BF16>(x, col, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density * inv_sd, lane, jx, scratch, lo, hi,
                               c_lo, c_hi, sl, total, unused))
-      warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density / sd, lane, jx, scratch, lo, hi,
+      warp_select<S, true>(x, n, P.keep - 1, P.keep - 1, P.key_q * sd, P.key_density * inv_sd, lane, jx, scratch, lo, hi,
                            c_lo, c_hi, sl, total, unused);
     res = __fadd_rn(__fdiv_rn(total, static_cast<float>(P.keep)), med);
   }
   return res;
+}
+
+// out-of-line copy for the packed kernel's rare fallback (keeps that kernel's hot loop small)
+template <int S, bool BF16>
+__device__ __noinline__ float general_column(const Params& P, const uint32_t* tile, int cw, int half, uint32_t* scratch,
+                                             int lane) {
+  return general_column_impl<S, BF16>(P, tile, cw, half, scratch, lane);
 }
 
 constexpr int kScratchWords = 320;             // per warp: candidate lists [8][32] words + two dense u16[64] arrays
@@ -540,7 +572,7 @@ trimmed_mean_kernel(const Params P) {
     for (int half = 0; half < (BF16 ? 2 : 1); ++half) {
       const int64_t col = col0 + (BF16 ? 2 * cw + half : cw);
       if (col >= P.d) break;                         // warp-uniform
-      const float res = general_column<S, BF16>(P, tile, cw, half, scratch, lane);
+      const float res = general_column_impl<S, BF16>(P, tile, cw, half, scratch, lane);
       if (lane == 0) P.out[col] = res;
     }
   }

@@ -1,8 +1,8 @@
-# final evidence refresh (single GPU)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 400 -p no:cacheprovider > gpurun_out/r02_z_pytest_all.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_z_smoke.txt 2>&1
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_z_bench_n1.json 2> gpurun_out/r02_z_bench_n1.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_z_launches_bench_n1.csv python bench.py --steps 2 --warmup 3 --extras off --no-cpu-baseline --e2e-steps 0 --no-parity > gpurun_out/r02_z_launches.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:gram_pair_kernel -s 1 -c 1 -o gpurun_out/r02_ncu_gram_pair_n1000 -f python tools/run_kernel.py pair1000 2 > gpurun_out/r02_z_ncu_pair.log 2>&1
-tail -3 gpurun_out/r02_z_pytest_all.txt; tail -1 gpurun_out/r02_z_smoke.txt; tail -c 300 gpurun_out/r02_z_bench_n1.err
+timeout 900 python -m pytest tests -m gpu -q --timeout 400 -p no:cacheprovider -k "trimmed or bulyan or golden or smoke or harness or properties" > gpurun_out/r02_z_pytest.txt 2>&1
+B="--extras off --no-cpu-baseline --e2e-steps 0"
+timeout 300 python bench.py --rule TrimmedMean --clients 1000 --dim 10000000 --dtype bf16 --steps 5 $B > gpurun_out/r02_z_tm_c3.json 2> gpurun_out/r02_z_tm_c3.err
+timeout 300 python bench.py --rule TrimmedMean --clients 1000 --dim 4000000 --dtype f32 --steps 5 $B > gpurun_out/r02_z_tm_f32.json 2> gpurun_out/r02_z_tm_f32.err
+timeout 300 python bench.py --rule Bulyan --clients 500 --dim 2500000 --byzantine 100 --steps 5 $B > gpurun_out/r02_z_bulyan500.json 2> gpurun_out/r02_z_bulyan500.err
+tail -3 gpurun_out/r02_z_pytest.txt
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:trimmed_mean_kernel -s 1 -c 1 -o gpurun_out/r02_ncu_tm_general_bf16_v4 -f python tools/run_kernel.py tm_bf16 2 > gpurun_out/r02_z_ncu_tm.log 2>&1
