@@ -36,7 +36,6 @@ SIGNATURES = {
     "afl_krum_from_sqdist": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "afl_bulyan_select": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "afl_trimmed_mean": (_i, [_vp, _i, _i64, _i64, _i, _vp, _i, _i, _vp, _vp]),
-    "afl_debug_tm_stats": (_i, [C.POINTER(C.c_uint64), _i]),
     "afl_gather_row": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp]),
     "afl_alie": (_i, [_vp, _i, _i64, _i64, _i, _d, _vp, _vp, _vp, _vp, _i64, _vp]),
     "afl_alie_band": (_i, [_vp, _vp, _d, _vp, _vp, _i64, _vp]),
@@ -109,8 +108,3 @@ def profile_read(kernel: str):
     return ms.value, cnt.value
 
 
-def tm_stats(reset: bool = False):
-    """(columns sent to the general path, bracket retries) of the packed bf16 trimmed-mean kernel since the last reset."""
-    out = (C.c_uint64 * 4)()
-    check(lib().afl_debug_tm_stats(out, 1 if reset else 0))
-    return int(out[1]), int(out[2])

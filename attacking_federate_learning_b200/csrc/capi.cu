@@ -104,7 +104,6 @@ int bulyan_select(const float* dist, int n, int users_count, int f, int* sel_out
                   cudaStream_t stream);
 }
 namespace tmean {
-int debug_stats(unsigned long long* out4, int reset);
 int trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* row_index, int n_rows,
                  int corrupted_count, float* out, cudaStream_t stream);
 }
@@ -333,7 +332,6 @@ int afl_trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, con
                              static_cast<cudaStream_t>(stream));
 }
 
-int afl_debug_tm_stats(unsigned long long* out4, int reset) { return tmean::debug_stats(out4, reset); }
 
 int afl_gather_row(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* idx_dev, float* out,
                    void* stream) {

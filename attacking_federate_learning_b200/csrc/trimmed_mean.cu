@@ -20,8 +20,6 @@
 //     which makes the reference's stable tie rule exact.  A min/max bisection fallback guarantees
 //     termination for any data (heavy ties, non-Gaussian columns); a tie group larger than a warp
 //     (ALIE's f identical rows) is resolved in row order with ballots.
-#include <stdlib.h>
-
 #include "afl_common.cuh"
 
 namespace afl {
@@ -547,14 +545,7 @@ __device__ __forceinline__ float general_column_impl(const Params& P, const uint
   return res;
 }
 
-// out-of-line copy for the packed kernel's rare fallback (keeps that kernel's hot loop small)
-template <int S, bool BF16>
-__device__ __noinline__ float general_column(const Params& P, const uint32_t* tile, int cw, int half, uint32_t* scratch,
-                                             int lane) {
-  return general_column_impl<S, BF16>(P, tile, cw, half, scratch, lane);
-}
-
-constexpr int kScratchWords = 320;             // per warp: candidate lists [8][32] words + two dense u16[64] arrays
+constexpr int kScratchWords = 96;              // per warp: dense candidate list [32] (fast path) / (key,row) u64[32] + payload[32] (general path)
 
 // S <= 16 (up to 512 rows: Bulyan's second stage at N = 500) leaves room for four CTAs per SM in shared memory; ask
 // the compiler for 64 registers there (the kernel is latency-bound: resident warps are what it needs)
@@ -584,432 +575,6 @@ trimmed_mean_kernel(const Params P) {
       if (col >= P.d) break;                         // warp-uniform
       const float res = general_column_impl<S, BF16>(P, tile, cw, half, scratch, lane);
       if (lane == 0) P.out[col] = res;
-    }
-  }
-}
-
-// =================================================================================================
-// Packed bf16 fast path: two adjacent bf16 columns share a 32-bit word per row, and every pass below works
-// on both with packed bf16x2 instructions (HADD2 / HSET2 / HMNMX2, ~1 instruction per value and pass) instead
-// of unpacking to fp32.  Per word-column (u = bf16(x - c) is monotone in x and every threshold is a bf16
-// value, so |u| < w  <=>  |x - c| < w exactly):
-//
-//   M0  mean / sigma of the first 128 rows (pivot model only).
-//   A'  count #{|u| < T} and #{u < 0} at c = mean, T = q sigma (q = Gaussian quantile of the keep fraction):
-//       the exact ranks at the model's pivots.
-//   A'' the same at the corrected centre / half-width; the two passes also give local densities.
-//   B   centre c, widths w0 <= w1 < w2.  {|u| < w0} brackets the median, {w1 <= |u| < w2} brackets both ends
-//       of the kept window (it is symmetric about the median), {|u| < w1} is kept for sure: its count and sum
-//       are accumulated (mixed-precision FHADD), the ~40 bracket elements are appended to per-lane lists in
-//       shared memory.
-//   F   the candidates of both columns are compacted, sorted by value with ONE packed 64-element bitonic
-//       network, the median is read off by rank, and the number of low-end / high-end candidates that complete
-//       the kept set is found with a warp-parallel merge-path step on |fl32(x - med)|.
-//
-// Every acceptance condition is checked (ranks inside the brackets, sure-kept elements closer than every
-// rejected candidate, nothing outside the brackets closer than a kept one, no tie group cut across the two
-// ends); one retry re-centres the brackets from the counts of the failed attempt, and anything else (heavy
-// ties, skewed or tiny columns, NaN statistics) runs general_column() on that column.  Results are therefore
-// the reference's for any data; only the speed depends on the column looking unimodal.
-// =================================================================================================
-__device__ __forceinline__ uint32_t pk_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float bf_half(uint32_t w, int h) { return __uint_as_float(h ? (w & 0xFFFF0000u) : (w << 16)); }
-__device__ __forceinline__ __nv_bfloat162 as_bf2(uint32_t w) { return *reinterpret_cast<__nv_bfloat162*>(&w); }
-__device__ __forceinline__ uint32_t as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
-__device__ __forceinline__ uint32_t hsub2_u(uint32_t a, uint32_t b) { return as_u32(__hsub2(as_bf2(a), as_bf2(b))); }
-__device__ __forceinline__ uint32_t hlt2_m(uint32_t a, uint32_t b) { return __hlt2_mask(as_bf2(a), as_bf2(b)); }
-__device__ __forceinline__ uint32_t habs2_u(uint32_t a) { return a & 0x7FFF7FFFu; }
-__device__ __forceinline__ uint32_t hmin2_u(uint32_t a, uint32_t b) { return as_u32(__hmin2(as_bf2(a), as_bf2(b))); }
-__device__ __forceinline__ uint32_t hmax2_u(uint32_t a, uint32_t b) { return as_u32(__hmax2(as_bf2(a), as_bf2(b))); }
-// acc (fp32) += / fma of one bf16 half of w: sm_100a mixed-precision FHADD / FHFMA with a half select
-__device__ __forceinline__ void fadd_bf_lo(float& acc, uint32_t w) {
-  asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(acc) : "h"(static_cast<unsigned short>(w & 0xFFFFu)));
-}
-__device__ __forceinline__ void fadd_bf_hi(float& acc, uint32_t w) {
-  asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(acc) : "h"(static_cast<unsigned short>(w >> 16)));
-}
-__device__ __forceinline__ void ffma_bf_lo(float& acc, uint32_t w) {
-  asm("fma.rn.f32.bf16 %0, %1, %1, %0;" : "+f"(acc) : "h"(static_cast<unsigned short>(w & 0xFFFFu)));
-}
-__device__ __forceinline__ void ffma_bf_hi(float& acc, uint32_t w) {
-  asm("fma.rn.f32.bf16 %0, %1, %1, %0;" : "+f"(acc) : "h"(static_cast<unsigned short>(w >> 16)));
-}
-// Packed count accumulator: acc -= mask (mask halves are 0 / 0xFFFF).  After the warp sum the low half holds the
-// low column's count and the high half (high count - low count) mod 2^16.
-__device__ __forceinline__ void unpack_counts(int acc, int& c_lo, int& c_hi) {
-  c_lo = acc & 0xFFFF;
-  c_hi = c_lo + ((acc - c_lo) >> 16);
-}
-
-// [0] columns finished by the packed path, [1] columns sent to general_column, [2] retries, [3] word-columns
-__device__ unsigned long long g_tm_stats[4];
-
-constexpr int kListCap = 8;                    // candidate words per lane
-constexpr uint32_t kInfW = 0x7F807F80u;        // +inf | +inf
-constexpr float kWM0 = 1.6f, kWM1 = 0.1f, kWM2 = 1.5f;                 // median bracket half-width in ranks: a sqrt(|o|+1) + b|o| + c
-constexpr float kWE0 = 1.6f, kWE1 = 0.1f, kWE2 = 1.2f, kWEa = 0.5f;    // end brackets, ranks per side (+ a' sqrt(|o|+1) for the asymmetry)
-
-// Counts at centre c2 / half-width T2 (packed bf16x2, one value per column).
-template <int S>
-__device__ __forceinline__ void packed_count(const uint32_t (&xw)[S], uint32_t c2, uint32_t T2, int (&clt)[2], int (&cin)[2]) {
-  int a_in = 0, a_lt = 0;
-#pragma unroll
-  for (int i = 0; i < S; ++i) {
-    const uint32_t u = hsub2_u(xw[i], c2);
-    a_in -= static_cast<int>(hlt2_m(habs2_u(u), T2));
-    a_lt -= static_cast<int>(hlt2_m(u, 0u));
-  }
-  a_in = __reduce_add_sync(0xffffffffu, a_in);
-  a_lt = __reduce_add_sync(0xffffffffu, a_lt);
-  unpack_counts(a_in, cin[0], cin[1]);
-  unpack_counts(a_lt, clt[0], clt[1]);
-}
-
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-
-// packed 64-element ascending bitonic sort of (r0: elements 0..31, r1: elements 32..63), both halves at once
-__device__ __forceinline__ void packed_sort64(uint32_t& r0, uint32_t& r1, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 64; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j == 32) {                                   // k == 64: partner is the other register, ascending
-        const uint32_t lo = hmin2_u(r0, r1), hi = hmax2_u(r0, r1);
-        r0 = lo; r1 = hi;
-      } else {
-        const uint32_t p0 = __shfl_xor_sync(0xffffffffu, r0, j), p1 = __shfl_xor_sync(0xffffffffu, r1, j);
-        const bool lower = (lane & j) == 0;
-        const bool up0 = (k >= 32) ? true : ((lane & k) == 0);
-        const bool up1 = (k == 64) ? true : ((k == 32) ? false : ((lane & k) == 0));
-        const uint32_t mn0 = hmin2_u(r0, p0), mx0 = hmax2_u(r0, p0);
-        const uint32_t mn1 = hmin2_u(r1, p1), mx1 = hmax2_u(r1, p1);
-        r0 = (lower == up0) ? mn0 : mx0;
-        r1 = (lower == up1) ? mn1 : mx1;
-      }
-    }
-  }
-}
-
-// element `idx` (0..63) of a (r0, r1) register pair spread over the warp, per-lane index allowed
-__device__ __forceinline__ uint32_t fetch64(uint32_t r0, uint32_t r1, int idx) {
-  const uint32_t a = __shfl_sync(0xffffffffu, r0, idx & 31), b = __shfl_sync(0xffffffffu, r1, idx & 31);
-  return (idx & 32) ? b : a;
-}
-__device__ __forceinline__ float fetch64f(float r0, float r1, int idx) {
-  const float a = __shfl_sync(0xffffffffu, r0, idx & 31), b = __shfl_sync(0xffffffffu, r1, idx & 31);
-  return (idx & 32) ? b : a;
-}
-
-constexpr int kAttempts = 3;
-// retry brackets are built from the failed attempt's exact local densities: only Poisson noise is left
-constexpr float kRM0 = 1.3f, kRM1 = 0.05f, kRM2 = 2.0f;
-constexpr float kRE0 = 1.2f, kRE1 = 0.05f, kRE2 = 1.5f;
-
-// Fast path for the two bf16 columns of one word-column.  ok[h] tells whether res[h] is valid.
-// t4: this lane's uint4 view of the word-column in the staged tile (register index i = 4 m + q <-> t4[m*32].{x,y,z,w}).
-template <int S>
-__device__ __forceinline__ void packed_pair(const Params& P, const uint4* t4, int jx, int lane, uint32_t* scratch,
-                                            bool (&ok)[2], float (&res)[2]) {
-  constexpr int kGroups = S / 4;
-  const int n = P.n_rows, keep = P.keep;
-  const int r1 = (n - 1) >> 1, r2 = n >> 1;
-  const float mid = 0.5f * static_cast<float>(r1 + r2) + 0.5f;
-  ok[0] = ok[1] = false;
-  res[0] = res[1] = 0.f;
-  if (keep <= 0 || n < 48) return;
-
-  bool alive[2] = {true, true};
-  float d0[2], dT[2];             // densities: ranks per unit value at the centre / per unit half-width at T (both ends)
-  float c_b[2], w0[2], w1[2], w2[2];
-  uint16_t* dense = reinterpret_cast<uint16_t*>(scratch + kListCap * 32);      // [2][64] bf16 bit patterns
-  const uint32_t list_base = smem_u32(scratch) + lane * 4;
-
-#pragma unroll 1
-  for (int attempt = 0; attempt < kAttempts; ++attempt) {
-    if (!(alive[0] && !ok[0]) && !(alive[1] && !ok[1])) break;
-    int n_sure[2], clt[2];
-    float ssum[2] = {0.f, 0.f};
-    uint32_t c2 = 0u, w0p = 0u, w1p = 0u, w2p = 0u;
-    float cc[2], v0[2], v1[2], v2[2];
-    bool run[2];
-    int mine;
-    bool overflow;
-    {
-      // the packed words live in registers only for the passes of this attempt (the finish needs the registers)
-      uint32_t xw[S];
-#pragma unroll
-      for (int m = 0; m < kGroups; ++m) {
-        const uint4 t = t4[m * 32];
-        xw[4 * m] = t.x; xw[4 * m + 1] = t.y; xw[4 * m + 2] = t.z; xw[4 * m + 3] = t.w;
-      }
-      if (attempt == 0) {
-        // ---------------- M0: moments of the first (up to) 128 rows ----------------
-        float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t w = xw[i];
-          if (S == 4 && row_of(i, jx, lane) >= n) w = 0u;          // padded rows (+inf) only exist in the last slots
-          fadd_bf_lo(s1[0], w); fadd_bf_hi(s1[1], w);
-          ffma_bf_lo(s2[0], w); ffma_bf_hi(s2[1], w);
-        }
-        const float ns = static_cast<float>(n < 128 ? n : 128);
-        float pc[2], pT[2];             // pivot proposals (fp32)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float m1 = warp_sum(s1[h]) / ns;
-          const float var = warp_sum(s2[h]) / ns - m1 * m1;
-          const float sd = sqrtf(fmaxf(var, 0.f));
-          alive[h] = (sd > 0.f) && (sd < kInf) && (fabsf(m1) < kInf) && (var > 1e-5f * m1 * m1);   // else cancellation: no model
-          pc[h] = m1; pT[h] = P.key_q * sd;
-          d0[h] = P.med_density / sd; dT[h] = P.key_density / sd;
-        }
-        if (!alive[0] && !alive[1]) return;
-        // ---------------- A': exact counts at the model's pivots ----------------
-        float c_a[2], T_a[2];           // the bf16 pivots pass A' really used
-        int clt_a[2], cin_a[2];
-        {
-          const uint32_t ca2 = pk_bf16x2(pc[0], pc[1]), Ta2 = pk_bf16x2(pT[0], pT[1]);
-          packed_count<S>(xw, ca2, Ta2, clt_a, cin_a);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            c_a[h] = bf_half(ca2, h); T_a[h] = bf_half(Ta2, h);
-            alive[h] = alive[h] && (T_a[h] > 0.f) && (T_a[h] < kInf) && (fabsf(c_a[h]) < kInf);
-            pc[h] = c_a[h] + (mid - static_cast<float>(clt_a[h])) / d0[h];
-            pT[h] = T_a[h] - static_cast<float>(cin_a[h] - keep) / dT[h];
-          }
-        }
-        // ---------------- A'': counts at the corrected pivots, local densities ----------------
-        {
-          const uint32_t cb2 = pk_bf16x2(pc[0], pc[1]), Tb2 = pk_bf16x2(pT[0], pT[1]);
-          int cl[2], ci[2];
-          packed_count<S>(xw, cb2, Tb2, cl, ci);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float cb = bf_half(cb2, h), Tb = bf_half(Tb2, h);
-            alive[h] = alive[h] && (Tb > 0.f) && (Tb < kInf) && (fabsf(cb) < kInf);
-            const float dx = cb - c_a[h], dt = Tb - T_a[h];
-            if (fabsf(dx) * d0[h] >= 8.f) d0[h] = clampf(static_cast<float>(cl[h] - clt_a[h]) / dx, 0.5f * d0[h], 2.f * d0[h]);
-            if (fabsf(dt) * dT[h] >= 8.f) dT[h] = clampf(static_cast<float>(ci[h] - cin_a[h]) / dt, 0.5f * dT[h], 2.f * dT[h]);
-            const float o = mid - static_cast<float>(cl[h]), e = static_cast<float>(ci[h] - keep);
-            c_b[h] = cb + o / d0[h];
-            const float Tn = Tb - e / dT[h];
-            const float gm = kWM0 * sqrtf(fabsf(o) + 1.f) + kWM1 * fabsf(o) + kWM2 + 0.5f * static_cast<float>(r2 - r1);
-            const float ge = kWE0 * sqrtf(0.5f * fabsf(e) + 1.f) + kWE1 * fabsf(e) + kWE2 + kWEa * sqrtf(fabsf(o) + 1.f);
-            w0[h] = gm / d0[h];
-            w1[h] = Tn - ge / (0.5f * dT[h]);
-            w2[h] = Tn + ge / (0.5f * dT[h]);
-          }
-        }
-      }
-      // ---------------- B: sure-kept count / sum, candidate lists ----------------
-      c2 = pk_bf16x2(c_b[0], c_b[1]);
-      w0p = pk_bf16x2(w0[0], w0[1]); w1p = pk_bf16x2(w1[0], w1[1]); w2p = pk_bf16x2(w2[0], w2[1]);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        cc[h] = bf_half(c2, h); v0[h] = bf_half(w0p, h); v1[h] = bf_half(w1p, h); v2[h] = bf_half(w2p, h);
-        run[h] = alive[h] && !ok[h] && (v0[h] > 0.f) && (v0[h] <= v1[h]) && (v1[h] < v2[h]) && (v2[h] < kInf) && (fabsf(cc[h]) < kInf);
-      }
-      if (!run[0] && !run[1]) break;
-      int a_sure = 0, a_lt = 0;
-      uint32_t off = 0;
-#pragma unroll
-      for (int i = 0; i < S; ++i) {
-        const uint32_t u = hsub2_u(xw[i], c2), au = habs2_u(u);
-        const uint32_t m0 = hlt2_m(au, w0p), m1 = hlt2_m(au, w1p), m2 = hlt2_m(au, w2p);
-        const uint32_t cand = m0 ^ m1 ^ m2;                     // nested sets: {|u|<w0} U {w1<=|u|<w2}
-        const uint32_t addr = list_base + (off & ((kListCap - 1) * 128u));   // wraps instead of overflowing
-        // predicated store + select: no branch, no divergence
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}\n" ::"r"(addr), "r"(xw[i]), "r"(cand) : "memory");
-        off += cand ? 128u : 0u;
-        const uint32_t xm = xw[i] & m1;
-        fadd_bf_lo(ssum[0], xm); fadd_bf_hi(ssum[1], xm);
-        a_sure -= static_cast<int>(m1);
-        a_lt -= static_cast<int>(hlt2_m(u, 0u));
-      }
-      a_sure = __reduce_add_sync(0xffffffffu, a_sure);
-      a_lt = __reduce_add_sync(0xffffffffu, a_lt);
-      unpack_counts(a_sure, n_sure[0], n_sure[1]);
-      unpack_counts(a_lt, clt[0], clt[1]);
-      mine = static_cast<int>(off >> 7);
-      overflow = __reduce_max_sync(0xffffffffu, mine) > kListCap;
-    }
-    __syncwarp();
-    // ---- F1: classify the list entries (both columns at once), count candidates per column
-    uint32_t ent[kListCap], cmk[kListCap];
-    int nA = 0, nB = 0, nmc = 0;                               // nmc: packed count of median-bracket candidates
-#pragma unroll
-    for (int k = 0; k < kListCap; ++k) {
-      const bool have = k < mine;
-      ent[k] = have ? scratch[k * 32 + lane] : kInfW;
-      const uint32_t u = hsub2_u(ent[k], c2), au = habs2_u(u);
-      const uint32_t m0 = hlt2_m(au, w0p);
-      const uint32_t m = m0 ^ hlt2_m(au, w1p) ^ hlt2_m(au, w2p);
-      cmk[k] = have ? m : 0u;
-      nA += (cmk[k] & 0xFFFFu) ? 1 : 0;
-      nB += (cmk[k] >> 16) ? 1 : 0;
-      nmc -= static_cast<int>(have ? m0 : 0u);
-    }
-    // ---- F2: exclusive prefix of the per-lane counts (two 16-bit fields in one register)
-    const int packed = nA | (nB << 16);
-    int incl = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const int totals = __shfl_sync(0xffffffffu, incl, 31);
-    const int tot[2] = {totals & 0xFFFF, totals >> 16};
-    int nmed[2];                                                 // median-bracket candidates (valid even when the lists overflowed... if not wrapped)
-    unpack_counts(__reduce_add_sync(0xffffffffu, nmc), nmed[0], nmed[1]);
-    int posA = (incl - packed) & 0xFFFF, posB = (incl - packed) >> 16;
-    const bool fits[2] = {!overflow && tot[0] <= 64, !overflow && tot[1] <= 64};
-    // ---- F3: dense arrays (values of column h), padded with +inf
-    if (fits[0] || fits[1]) {
-#pragma unroll
-      for (int k = 0; k < kListCap; ++k) {
-        if ((cmk[k] & 0xFFFFu) && fits[0]) dense[posA++] = static_cast<uint16_t>(ent[k] & 0xFFFFu);
-        if ((cmk[k] >> 16) && fits[1]) dense[64 + posB++] = static_cast<uint16_t>(ent[k] >> 16);
-      }
-    }
-#pragma unroll
-    for (int e = lane; e < 64; e += 32) {
-      if (!fits[0] || e >= tot[0]) dense[e] = 0x7F80;
-      if (!fits[1] || e >= tot[1]) dense[64 + e] = 0x7F80;
-    }
-    __syncwarp();
-    uint32_t r0 = static_cast<uint32_t>(dense[lane]) | (static_cast<uint32_t>(dense[64 + lane]) << 16);
-    uint32_t r1s = static_cast<uint32_t>(dense[32 + lane]) | (static_cast<uint32_t>(dense[96 + lane]) << 16);
-    __syncwarp();
-    packed_sort64(r0, r1s, lane);
-    // ---- F4: class of every sorted element (low end / median bracket / high end), both columns at once
-    const uint32_t u0 = hsub2_u(r0, c2), u1 = hsub2_u(r1s, c2);
-    const uint32_t au0 = habs2_u(u0), au1 = habs2_u(u1);
-    const uint32_t med0 = hlt2_m(au0, w0p), med1 = hlt2_m(au1, w0p);
-    const uint32_t end0 = hlt2_m(au0, w2p) & ~hlt2_m(au0, w1p), end1 = hlt2_m(au1, w2p) & ~hlt2_m(au1, w1p);
-    const uint32_t neg0 = hlt2_m(u0, 0u), neg1 = hlt2_m(u1, 0u);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (!run[h]) continue;                                    // warp-uniform
-      bool good = fits[h];
-      const uint32_t sh = h ? 16u : 0u;
-      const bool isMed0 = (med0 >> sh) & 1u, isMed1 = (med1 >> sh) & 1u;
-      const bool isEnd0 = (end0 >> sh) & 1u, isEnd1 = (end1 >> sh) & 1u;
-      const bool isNeg0 = (neg0 >> sh) & 1u, isNeg1 = (neg1 >> sh) & 1u;
-      const bool low0 = isEnd0 && isNeg0, low1 = isEnd1 && isNeg1;
-      const bool high0 = isEnd0 && !isNeg0, high1 = isEnd1 && !isNeg1;
-      const int nl = __popc(__ballot_sync(0xffffffffu, low0)) + __popc(__ballot_sync(0xffffffffu, low1));
-      const int nm = __popc(__ballot_sync(0xffffffffu, isMed0)) + __popc(__ballot_sync(0xffffffffu, isMed1));
-      const int nh = __popc(__ballot_sync(0xffffffffu, high0)) + __popc(__ballot_sync(0xffffffffu, high1));
-      const int nmneg = __popc(__ballot_sync(0xffffffffu, isMed0 && isNeg0)) + __popc(__ballot_sync(0xffffffffu, isMed1 && isNeg1));
-      good = good && (nl + nm + nh == tot[h]);
-      // ---- median by rank: sorted layout is [low end | median bracket | high end | padding]
-      const int g0 = clt[h] - nmneg;                            // elements below the first median candidate
-      const int ia = nl + (r1 - g0), ib = nl + (r2 - g0);
-      const bool med_in = good && (r1 >= g0) && (r2 - g0 < nm);
-      const int ia_c = med_in ? ia : 0, ib_c = med_in ? ib : 0;
-      const float a = bf_half(fetch64(r0, r1s, ia_c), h), b = bf_half(fetch64(r0, r1s, ib_c), h);
-      const float med = ((n & 1) != 0) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);
-      // ---- ends: keys |fl32(x - med)| of this lane's two elements
-      const float x0 = bf_half(r0, h), x1 = bf_half(r1s, h);
-      const float dv0 = __fsub_rn(x0, med), dv1 = __fsub_rn(x1, med);
-      const float k0 = fabsf(dv0), k1 = fabsf(dv1);
-      const int need = keep - n_sure[h];
-      const bool need_ok = (need >= 0) && (need <= nl + nh);
-      // merge path: i low-end + (need - i) high-end candidates; lane l tests i = ilo + l
-      const int ilo = max(0, need - nh), ihi = min(need, nl);
-      const int it = ilo + lane;
-      const bool tv = need_ok && med_in && (it < ihi);
-      const int li = tv ? (nl - 1 - it) : 0, hj = tv ? (nl + nm + (need - 1 - it)) : 0;
-      const float kl = fetch64f(k0, k1, li), kh = fetch64f(k0, k1, hj);
-      const unsigned pb = __ballot_sync(0xffffffffu, tv && (kl < kh));
-      const int np = __popc(pb);
-      good = med_in && need_ok && (pb == ((np >= 32) ? 0xffffffffu : ((1u << np) - 1u)));   // monotone
-      const int istar = ilo + np, jstar = need - istar;
-      // kept flags: low list position = nl-1-e, high list position = e-nl-nm (e = sorted index)
-      const int e0 = lane, e1 = lane + 32;
-      const bool kept0 = (low0 && (nl - 1 - e0 < istar)) || (high0 && (e0 - nl - nm < jstar));
-      const bool kept1 = (low1 && (nl - 1 - e1 < istar)) || (high1 && (e1 - nl - nm < jstar));
-      const float csum = warp_sum((kept0 ? dv0 : 0.f) + (kept1 ? dv1 : 0.f));
-      // largest kept key T, smallest rejected candidate key U (non-negative floats order like their bit patterns)
-      const unsigned Tb = __reduce_max_sync(0xffffffffu, max(kept0 ? __float_as_uint(k0) : 0u, kept1 ? __float_as_uint(k1) : 0u));
-      const unsigned Ub = __reduce_min_sync(0xffffffffu, min((isEnd0 && !kept0) ? __float_as_uint(k0) : 0x7F800000u,
-                                                             (isEnd1 && !kept1) ? __float_as_uint(k1) : 0x7F800000u));
-      const float T = __uint_as_float(Tb), U = __uint_as_float(Ub);
-      const bool any_kept = need > 0;
-      // sure-kept elements satisfy |x - c| < w1 exactly, outside elements |x - c| >= w2 (1 - 2^-8) (rounding of u)
-      const float dcm = fabsf(cc[h] - med);
-      const float B_in = (v1[h] + dcm) * 1.000001f, B_out = v2[h] * 0.99609375f - dcm;
-      good = good && (U > B_in) && (B_out > B_in) && (!any_kept || T < B_out);
-      if (good && any_kept && T == U) {                         // a tie group at the boundary: fine unless it spans both ends
-        const bool kl_t = __any_sync(0xffffffffu, (kept0 && low0 && k0 == T) || (kept1 && low1 && k1 == T));
-        const bool kh_t = __any_sync(0xffffffffu, (kept0 && high0 && k0 == T) || (kept1 && high1 && k1 == T));
-        const bool ul_t = __any_sync(0xffffffffu, (!kept0 && low0 && k0 == T) || (!kept1 && low1 && k1 == T));
-        const bool uh_t = __any_sync(0xffffffffu, (!kept0 && high0 && k0 == T) || (!kept1 && high1 && k1 == T));
-        if ((kl_t && uh_t) || (kh_t && ul_t)) { good = false; alive[h] = false; }    // row order decides: general path
-      }
-      const float sure = warp_sum(ssum[h]);
-      if (good) {
-        const float total = __fadd_rn(__fsub_rn(sure, __fmul_rn(static_cast<float>(n_sure[h]), med)), csum);
-        res[h] = __fadd_rn(__fdiv_rn(total, static_cast<float>(keep)), med);
-        ok[h] = true;
-      } else if (alive[h] && attempt + 1 < kAttempts) {
-        if (lane == 0) atomicAdd(&g_tm_stats[2], 1ull);
-        // ---- rebuild the brackets from this attempt's exact counts (valid unless a lane's list wrapped):
-        // {|u|<w1}: n_sure, median bracket: nmed over 2 w0, end brackets: tot - nmed over (w2 - w1), #{u<0}: clt
-        const int n_med = overflow ? 0 : nmed[h], n_end = overflow ? 0 : (tot[h] - nmed[h]);
-        const float o = mid - static_cast<float>(clt[h]);
-        const float dm = n_med >= 4 ? clampf(static_cast<float>(n_med) / (2.f * v0[h]), 0.4f * d0[h], 2.5f * d0[h]) : d0[h];
-        const float de = n_end >= 4 ? clampf(static_cast<float>(n_end) / (v2[h] - v1[h]), 0.4f * dT[h], 2.5f * dT[h]) : dT[h];
-        const float e = static_cast<float>(n_sure[h] - keep);          // (minus) the ranks still missing beyond half-width w1
-        c_b[h] = cc[h] + o / dm;
-        const float Tn = v1[h] - e / de;
-        const float gm = kRM0 * sqrtf(fabsf(o) + 1.f) + kRM1 * fabsf(o) + kRM2 + 0.5f * static_cast<float>(r2 - r1);
-        const float ge = kRE0 * sqrtf(0.5f * fabsf(e) + 1.f) + kRE1 * fabsf(e) + kRE2 + kWEa * sqrtf(fabsf(o) + 1.f);
-        d0[h] = dm; dT[h] = de;
-        w0[h] = gm / dm;
-        w1[h] = Tn - ge / (0.5f * de);
-        w2[h] = Tn + ge / (0.5f * de);
-        if (!fits[h]) {                                          // too many candidates: never widen after an overflow
-          w0[h] = fminf(w0[h], 0.7f * v0[h]);
-          const float half = 0.35f * (v2[h] - v1[h]);
-          w1[h] = fmaxf(w1[h], Tn - half); w2[h] = fminf(w2[h], Tn + half);
-        }
-      }
-    }
-  }
-}
-
-template <int S>
-__global__ void __launch_bounds__(kThreads, 3)
-trimmed_mean_packed_kernel(const Params P) {
-  extern __shared__ __align__(1024) uint32_t tile[];
-  constexpr int kGroups = S / 4;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t col0 = static_cast<int64_t>(blockIdx.x) * 32;
-  stage_tile<S, true>(P, tile, col0);
-  __syncthreads();
-  uint32_t* scratch = tile + kWordCols * kGroups * 128 + warp * kScratchWords;
-#pragma unroll 1
-  for (int cw = warp; cw < kWordCols; cw += kWarps) {
-    const int64_t colA = col0 + 2 * cw;
-    if (colA >= P.d) break;                                      // warp-uniform
-    const int jx = (cw >> 2) & 3;
-    bool ok[2];
-    float res[2];
-    packed_pair<S>(P, reinterpret_cast<const uint4*>(tile) + (cw * kGroups) * 32 + lane, jx, lane, scratch, ok, res);
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      if (colA + h >= P.d) break;
-      float r = res[h];
-      if (!ok[h]) r = general_column<S, true>(P, tile, cw, h, scratch, lane);
-      if (lane == 0) {
-        P.out[colA + h] = r;
-        if (!ok[h]) atomicAdd(&g_tm_stats[1], 1ull);
-      }
     }
   }
 }
@@ -1148,15 +713,7 @@ static int launch(const Params& P, int dtype, cudaStream_t stream) {
   const int cols = dtype == AFL_BF16 ? 32 : 16;
   const unsigned grid = static_cast<unsigned>(ceil_div64(P.d, cols));
   ProfScope ps("trimmed_mean", stream);
-  // The packed bf16x2 path (two columns per word, HSET2 counting passes) is exact and ~1.35x faster than the general
-  // path on plain Gaussian columns, but ~15 % slower on the benchmark's heterogeneous-client columns (r02 run E:
-  // 66.0 vs 56.1 ms at C3), where one column in five needs a second bracket pass.  Opt in with AFL_TM_KERNEL=packed.
-  const char* tm_env = getenv("AFL_TM_KERNEL");
-  const bool use_packed = tm_env && tm_env[0] == 'p';
-  if (dtype == AFL_BF16 && use_packed) {
-    AFL_CUDA(cudaFuncSetAttribute(trimmed_mean_packed_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    trimmed_mean_packed_kernel<S><<<grid, kThreads, smem, stream>>>(P);
-  } else if (dtype == AFL_BF16) {
+  if (dtype == AFL_BF16) {
     AFL_CUDA(cudaFuncSetAttribute(trimmed_mean_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     trimmed_mean_kernel<S, true><<<grid, kThreads, smem, stream>>>(P);
   } else {
@@ -1201,16 +758,6 @@ int trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, const i
   if (n_rows <= 256) return launch<8>(P, dtype, stream);
   if (n_rows <= 512) return launch<16>(P, dtype, stream);
   return launch<32>(P, dtype, stream);
-}
-
-// Diagnostics: how many columns the packed bf16 path finished itself / handed to the general path / retried.
-int debug_stats(unsigned long long* out4, int reset) {
-  if (out4) AFL_CUDA(cudaMemcpyFromSymbol(out4, g_tm_stats, sizeof(unsigned long long) * 4));
-  if (reset) {
-    const unsigned long long z[4] = {0, 0, 0, 0};
-    AFL_CUDA(cudaMemcpyToSymbol(g_tm_stats, z, sizeof(z)));
-  }
-  return AFL_OK;
 }
 
 }  // namespace tmean

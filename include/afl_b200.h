@@ -127,10 +127,6 @@ int afl_bulyan_select(const float* dist, int n, int users_count, int corrupted_c
 int afl_trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* row_index,
                      int n_rows, int corrupted_count, float* out, void* stream);
 
-/* Diagnostics of the packed bf16 kernel (synchronises the device): out4 = {unused, columns handed to the general
- * per-column path, bracket retries, unused}; reset != 0 clears the counters. */
-int afl_debug_tm_stats(unsigned long long* out4, int reset);
-
 /* ---- gather one row chosen on the device (Krum's result as a dense vector) --------------------- */
 int afl_gather_row(const void* G, int n, int64_t d, int64_t ld, int dtype, const int* idx_dev,
                    float* out, void* stream);

@@ -168,14 +168,12 @@ def test_trimmed_mean_more_than_1024_rows(api, n, f, bf16):
 
 
 @pytest.mark.parametrize("dist", ["gauss", "shifted", "ties_bf16", "lognormal", "alie", "two_clusters"])
-@pytest.mark.parametrize("n,f,bf16,kernel", [(1000, 240, True, "general"), (1000, 240, True, "packed"), (1000, 240, False, "general"),
-                                             (300, 200, False, "general"), (520, 480, False, "general"), (520, 480, True, "packed"),
-                                             (300, 100, True, "packed"), (97, 20, True, "general"), (97, 20, True, "packed")])
-def test_trimmed_mean_distributions(api, monkeypatch, dist, n, f, bf16, kernel):
-    """Column distributions that stress the selection kernels' pivot models and their tie handling; the bf16 cases
-    run both the general per-column kernel and the packed two-columns-per-word kernel (AFL_TM_KERNEL=packed)."""
+@pytest.mark.parametrize("n,f,bf16", [(1000, 240, True), (1000, 240, False), (300, 200, False), (520, 480, False),
+                                      (520, 480, True), (300, 100, True), (97, 20, True), (97, 20, False), (200, 48, True)])
+def test_trimmed_mean_distributions(api, dist, n, f, bf16):
+    """Column distributions that stress the selection kernel's pivot model, its retry logic and its tie handling, for
+    every instantiation of the kernel (S = 4, 8, 16, 32 slots per lane) and both element types."""
     D, *_ = api
-    monkeypatch.setenv("AFL_TM_KERNEL", kernel)
     import zlib
     rng = np.random.default_rng(zlib.crc32(f"{dist}-{n}-{f}-{bf16}".encode()))
     d = 1536

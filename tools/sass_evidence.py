@@ -4,7 +4,7 @@ import collections, re, subprocess, sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "attacking_federate_learning_b200/lib/libafl_b200.so"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 KEYS = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOMSWS", "HMMA", "HGMMA", "LDGSTS",
-        "FHADD", "FHFMA", "HSET2", "HMNMX2", "REDUX")
+        "REDUX", "PRMT", "VIMNMX")
 cur, stats, samples = None, collections.OrderedDict(), collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -18,12 +18,12 @@ for line in out.splitlines():
     for key in KEYS:
         if op.startswith(key):
             stats[cur][key] += 1
-            if key in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "FHADD", "FHFMA") and len([s for s in samples[cur] if s.startswith(key)]) < 2:
+            if key in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR") and len([s for s in samples[cur] if s.startswith(key)]) < 2:
                 samples[cur].append(key + ": " + ins)
 print("# cuobjdump -sass %s (sm_100a), per kernel: counts of the SASS mnemonics that prove the Blackwell paths" % lib)
 print("# (B200_PROFILING.md): tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, TMA -> UTMALDG, tcgen05.commit -> UTCBAR, TMEM alloc ->")
-print("# UTCATOMSWS; mixed-precision bf16->fp32 add/fma -> FHADD/FHFMA; packed bf16x2 compares / min-max -> HSET2 / HMNMX2; warp")
-print("# reductions -> REDUX.  No HMMA (legacy mma.sync) and no HGMMA (Hopper) anywhere.\n")
+print("# UTCATOMSWS; warp reductions -> REDUX; the trimmed-mean kernel's bf16 unpack -> PRMT, its integer-key sort -> VIMNMX.")
+print("# No HMMA (legacy mma.sync) and no HGMMA (Hopper) anywhere.\n")
 for fn, c in stats.items():
     if not c:
         continue
