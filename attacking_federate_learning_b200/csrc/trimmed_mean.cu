@@ -498,7 +498,7 @@ __device__ __forceinline__ float general_column_impl(const Params& P, const uint
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < S; ++i) {
-    if (S >= 8 && i < S / 2) {             // the launcher picks S with 16 * S < n_rows for S >= 8
+    if (S >= 8 && i < S / 2) {             // the launcher picks S with 32 * 4 * ceil(S / 8) <= n_rows for S >= 8
       s1 += x[i]; s2 = fmaf(x[i], x[i], s2);
     } else {
       asm("{\n\t.reg .pred p;\n\t"
@@ -547,10 +547,10 @@ __device__ __forceinline__ float general_column_impl(const Params& P, const uint
 
 constexpr int kScratchWords = 96;              // per warp: dense candidate list [32] (fast path) / (key,row) u64[32] + payload[32] (general path)
 
-// S <= 16 (up to 512 rows: Bulyan's second stage at N = 500) leaves room for four CTAs per SM in shared memory; ask
-// the compiler for 64 registers there (the kernel is latency-bound: resident warps are what it needs)
+// S <= 20 (up to 640 rows: Bulyan's second stage at N = 500 and N = 1000) leaves room for four CTAs per SM in shared memory; ask
+// the compiler for 64 registers there (resident warps are what hides the shuffle chains of the scans and sorts)
 template <int S, bool BF16>
-__global__ void __launch_bounds__(kThreads, (S <= 16 ? 4 : 3))
+__global__ void __launch_bounds__(kThreads, (S <= 20 ? 4 : 3))      // (S = 24 fits 4 CTAs in shared memory too, but the fp32 instance spills at 64 registers)
 trimmed_mean_kernel(const Params P) {
   extern __shared__ __align__(1024) uint32_t tile[];     // [16 word-cols][S/4 groups][32 lanes][4 slots] + scratch
   constexpr int kGroups = S / 4;
@@ -754,9 +754,15 @@ int trimmed_mean(const void* G, int n, int64_t d, int64_t ld, int dtype, const i
     AFL_LAUNCH_CHECK("trimmed_mean_large_kernel");
     return AFL_OK;
   }
+  // S = slots per lane, a multiple of 4 with 32 * S >= n_rows: the work per column is proportional to S, not to n_rows
+  // (Bulyan's second stage at N = 1000, f = 240 selects 520 rows: S = 20 instead of 32)
   if (n_rows <= 128) return launch<4>(P, dtype, stream);
   if (n_rows <= 256) return launch<8>(P, dtype, stream);
+  if (n_rows <= 384) return launch<12>(P, dtype, stream);
   if (n_rows <= 512) return launch<16>(P, dtype, stream);
+  if (n_rows <= 640) return launch<20>(P, dtype, stream);
+  if (n_rows <= 768) return launch<24>(P, dtype, stream);
+  if (n_rows <= 896) return launch<28>(P, dtype, stream);
   return launch<32>(P, dtype, stream);
 }
 

@@ -169,10 +169,13 @@ def test_trimmed_mean_more_than_1024_rows(api, n, f, bf16):
 
 @pytest.mark.parametrize("dist", ["gauss", "shifted", "ties_bf16", "lognormal", "alie", "two_clusters"])
 @pytest.mark.parametrize("n,f,bf16", [(1000, 240, True), (1000, 240, False), (300, 200, False), (520, 480, False),
-                                      (520, 480, True), (300, 100, True), (97, 20, True), (97, 20, False), (200, 48, True)])
+                                      (520, 480, True), (300, 100, True), (97, 20, True), (97, 20, False), (200, 48, True),
+                                      (385, 90, True), (641, 150, False), (700, 170, True), (769, 180, False), (850, 200, True),
+                                      (897, 210, False)])
 def test_trimmed_mean_distributions(api, dist, n, f, bf16):
     """Column distributions that stress the selection kernel's pivot model, its retry logic and its tie handling, for
-    every instantiation of the kernel (S = 4, 8, 16, 32 slots per lane) and both element types."""
+    every instantiation of the kernel (S = 4, 8, ..., 32 slots per lane, incl. the first row count of a size class) and both
+    element types."""
     D, *_ = api
     import zlib
     rng = np.random.default_rng(zlib.crc32(f"{dist}-{n}-{f}-{bf16}".encode()))
