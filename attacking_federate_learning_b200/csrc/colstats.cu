@@ -102,9 +102,11 @@ mean_kernel(const T* __restrict__ G, int n, int64_t d, int64_t ld, float* __rest
     if (c0 + k < d) out[c0 + k] = __fdiv_rn(acc[k], fn);
 }
 
-// ---- ALIE: one pass, shifted moments (shift = the first malicious row, so |x - shift| ~ sigma and
-// E[dx^2] - E[dx]^2 does not cancel).  sigma = sqrt(population variance); crafted = mu - z*sigma with
-// the same two roundings as `grads_mean[:] -= num_std * grads_stdev[:]` in fp32.
+// ---- ALIE: one pass, sum(x) and sum(x^2) per column in FLOAT64 (B200 has a full-rate FP64 pipe: 3 FP64 instructions
+// per value hide under the HBM stream).  x*x is exact in float64 and the sums carry ~1e-16 relative error, so
+// E[x^2] - E[x]^2 is accurate even when one client is orders of magnitude larger than the column's sigma (the
+// round-1 version shifted by the first row in fp32 and lost ~1e-5 relative there).  sigma = sqrt(population
+// variance); crafted = mu - z*sigma with the same two fp32 roundings as `grads_mean[:] -= num_std * grads_stdev[:]`.
 template <typename T, int VEC, bool COHERENT>
 __global__ void __launch_bounds__(kBlock)
 alie_kernel(const T* G, int f, int64_t d, int64_t ld, float z, float* __restrict__ mu_out,
@@ -112,11 +114,10 @@ alie_kernel(const T* G, int f, int64_t d, int64_t ld, float z, float* __restrict
   const int64_t c0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * VEC;
   if (c0 >= d) return;
   const T* p = G + c0;
-  const Pack<VEC> shift = load_rows<T, VEC, COHERENT>(p);
-  float s1[VEC], s2[VEC];
+  double s1[VEC], s2[VEC];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-  int r = 1;
+  for (int k = 0; k < VEC; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
+  int r = 0;
   for (; r + kUnroll <= f; r += kUnroll) {
     Pack<VEC> t[kUnroll];
 #pragma unroll
@@ -125,29 +126,29 @@ alie_kernel(const T* G, int f, int64_t d, int64_t ld, float z, float* __restrict
     for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const float dx = t[u].v[k] - shift.v[k];
-        s1[k] += dx;
-        s2[k] = fmaf(dx, dx, s2[k]);
+        const double x = static_cast<double>(t[u].v[k]);
+        s1[k] += x;
+        s2[k] = fma(x, x, s2[k]);
       }
   }
   for (; r < f; ++r) {
     Pack<VEC> t = load_rows<T, VEC, COHERENT>(p + static_cast<int64_t>(r) * ld);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const float dx = t.v[k] - shift.v[k];
-      s1[k] += dx;
-      s2[k] = fmaf(dx, dx, s2[k]);
+      const double x = static_cast<double>(t.v[k]);
+      s1[k] += x;
+      s2[k] = fma(x, x, s2[k]);
     }
   }
-  const float inv = 1.0f / static_cast<float>(f);
+  const double inv = 1.0 / static_cast<double>(f);
   float crafted[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    const float m1 = s1[k] * inv;
-    const float mu = shift.v[k] + m1;
-    float var = fmaf(-m1, m1, s2[k] * inv);
-    var = var > 0.f ? var : 0.f;
-    const float sigma = sqrtf(var);
+    const double m = s1[k] * inv;
+    double var = fma(-m, m, s2[k] * inv);
+    var = var > 0.0 ? var : 0.0;
+    const float mu = static_cast<float>(m);
+    const float sigma = static_cast<float>(sqrt(var));
     crafted[k] = __fsub_rn(mu, __fmul_rn(z, sigma));
     if (c0 + k < d) {
       if (sigma_out) sigma_out[c0 + k] = sigma;

@@ -50,25 +50,43 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (20 ms period)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md's clocks line, its 200 ms period) sampled while the step
+    loop runs.  Round 1 polled every 20 ms; a 2-GPU A/B (profiles/r02_clock_sampler_ab.json) showed that a query landing
+    inside a 10-20 ms timed region stalls kernel launches: 0.528 ms/step with the sampler off or at 200 ms, 0.535 or
+    0.682 ms at 20 ms - the "sporadic slow run" of the round-1 scaling table.  So: the timed region starts right after
+    a sample arrived (the next query is 200 ms away), and when the region is shorter than two periods the same step
+    loop keeps running, untimed, until two more samples are in (`run_config`), so the clocks are read under the
+    measured load without a query inside the measurement."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.period_ms = int(os.environ.get("AFL_BENCH_CLOCKS_MS", "200"))
 
     def start(self):
+        if self.period_ms <= 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
             t0 = time.time()
             while not self.rows and time.time() - t0 < 3.0:      # first sample before the timed region starts
-                time.sleep(0.01)
+                time.sleep(0.002)
         except Exception:
             self.proc = None
+
+    def align(self):
+        """Return right after the next sample arrived, so that the following period is free of queries."""
+        if self.proc is None:
+            return
+        n0, t0 = len(self.rows), time.time()
+        while len(self.rows) == n0 and time.time() - t0 < 1.0:
+            time.sleep(0.001)
+        self.first = len(self.rows)                              # samples from here on are taken under the step loop
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -80,7 +98,7 @@ class ClockSampler:
         time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[getattr(self, "first", 0):]:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 8:
                 continue
@@ -406,19 +424,30 @@ def run_config(cx, rule, n, d, f, dtype, steps, warmup, want_e2e=False, e2e_step
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if rank == 0:
+        sampler.align()               # the next nvidia-smi query is one period (200 ms) away
     barrier()
     e0.record()
     for _ in range(steps):
         out = step()
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = float(ms_total.item()) / steps
     launches = nat.launch_count() - launches0
     nat.profile_enable(False)
+    # clocks under load: keep the same step loop running (untimed, same count on every rank) until two sampler periods
+    # have passed since the timed region began
+    need_ms = 2.2 * sampler.period_ms - float(ms_total.item())
+    if need_ms > 0 and sampler.period_ms > 0:
+        for _ in range(min(5000, int(need_ms / max(ms_step, 1e-3)) + 1)):
+            step()
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["sampling"] = f"nvidia-smi -lms {sampler.period_ms}, samples from the start of the timed region to the end of the same step loop"
     dom = {}
     for kname in ("gram_bf16x2", "gram_pair", "gram_tcgen05", "sqdist_simt", "trimmed_mean", "mean", "alie"):
         k_ms, k_cnt = nat.profile_read(kname)
