@@ -68,3 +68,43 @@ def test_extra_configs_cover_the_baseline_configs():
     assert full["C5-krum"][1:3] == (1000, 25_000_000)           # N=1000 x D=25M fp32 = 100 GB fits one B200
     small = {t[-1]: t for t in bench.extra_configs(1, 60.0)}
     assert small["C5-krum"][2] < 25_000_000                      # otherwise the largest D that fits, stated in the record
+
+
+def test_clock_sampler_reads_only_samples_taken_after_align(tmp_path, monkeypatch):
+    """bench.py's nvidia-smi sampler: `align()` returns right after a sample (so the following period is free of
+    queries) and `stop()` reports only the samples taken from then on - checked with a stand-in `nvidia-smi` that
+    prints one row per period: 1000 MHz before the timed region, 1965 MHz once a flag file exists."""
+    import importlib.util
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    flag = tmp_path / "loaded"
+    fake.write_text(f"""#!{sys.executable}
+import os, sys, time
+period = int(sys.argv[sys.argv.index("-lms") + 1]) / 1000.0
+while True:
+    mhz = 1965 if os.path.exists({str(flag)!r}) else 1000
+    print(f"0, {{mhz}}, 1965, 700.0, Not Active, Not Active, Not Active, Active", flush=True)
+    time.sleep(period)
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}{os.pathsep}{os.environ['PATH']}")
+    monkeypatch.setenv("AFL_BENCH_CLOCKS_MS", "50")
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    assert s.period_ms == 50
+    s.start()
+    assert s.rows, "the first sample arrives before the timed region starts"
+    s.align()
+    flag.write_text("x")                     # "the step loop is running" from here on
+    time.sleep(0.25)
+    out = s.stop()
+    assert out["samples"] >= 2 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+    # period 0 switches the sampler off (A/B runs): no process, and stop() says so
+    monkeypatch.setenv("AFL_BENCH_CLOCKS_MS", "0")
+    off = bench.ClockSampler(0)
+    off.start(); off.align()
+    assert off.stop()["sm_mhz"] is None
