@@ -11,15 +11,20 @@
 //     [word-column][slot-group][lane] order with an XOR on the slot-in-group index, so that both the
 //     staging stores (STS.32) and the per-column reads (LDS.128) are bank-conflict free.
 //   * One warp then owns one word-column: lane l holds rows l, l+32, l+64, ... in registers
-//     (S = ceil(N/32) "slots"), so every pass over the column is pure register arithmetic plus one
-//     warp reduction.  Rows past N are staged as +inf and never counted.
-//   * Selection is an interpolation search on counts: a pass counts #{x < p} (and, for the |dev|
-//     threshold, the sum of the devs below p); the first pivot comes from the column's mean / sigma,
-//     later ones from the measured counts.  As soon as the bracket [lo, hi) holds <= 32 elements they
-//     are compacted (ballot) to one per lane and bitonic-sorted with the row index as secondary key,
-//     which makes the reference's stable tie rule exact.  A min/max bisection fallback guarantees
-//     termination for any data (heavy ties, non-Gaussian columns); a tie group larger than a warp
-//     (ALIE's f identical rows) is resolved in row order with ballots.
+//     (S slots per lane, S = 4, 8, 12, ..., 32: the smallest multiple of 4 with 32 S >= rows), so every pass over
+//     the column is pure register arithmetic plus one warp reduction.  Rows past N are staged as +inf.
+//   * Selection, fast path (select_fast): ONE fused pass per order statistic with a bracket [a, b) aimed from the
+//     column's mean / sigma (median) or sigma and the normal quantile (|dev| threshold): it counts #{key < a}, sums
+//     the devs below a, and marks the in-bracket slots in a per-lane bit mask (4-5 instructions per value, in PTX).
+//     When the target rank is inside and <= 32 slots are marked, the candidates are re-read from the tile by slot
+//     index, compacted to one per lane (shuffle scan) and sorted with a 15-stage shuffle bitonic network; otherwise
+//     the bracket is re-aimed from the measured counts (about one column in four needs a second pass).
+//   * Selection, general path (warp_select): interpolation search on counts with a min/max bisection fallback that
+//     terminates for any data (heavy ties, non-Gaussian columns); brackets of <= 32 elements are compacted by ballot
+//     and ranked on (key, row), which makes the reference's stable tie rule exact.  In the fast path a tie group that
+//     the keep boundary cuts (ALIE's f identical rows, bf16 value collisions) is resolved in row order with ballots on
+//     the register-resident column (tie_sum).
+//   * More than 1024 rows: trimmed_mean_large_kernel (shared-memory strip, bisection on the integer image of the keys).
 #include "afl_common.cuh"
 
 namespace afl {
